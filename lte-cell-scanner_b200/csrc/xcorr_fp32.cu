@@ -1,0 +1,335 @@
+// xcorr_fp32.cu - fused PSS correlator on the FP32 CUDA cores (general-input path).
+//
+// Replaces xc_correlate + xc_combine + xc_delay_spread + sp_est + xc_peak_freq of the reference
+// (src/searcher.cpp:113-383) with three kernels:
+//
+//   xcorr_fold_fp32   correlate the capture buffer against 3 PSS roots x n_f frequency hypotheses
+//                     (137 complex taps) and accumulate |xc|^2 over the n_comb half frames IN
+//                     REGISTERS - the 3 x (n_cap-136) x n_f complex `xc` array of the reference
+//                     (136 MB at n_f=37) is never materialised.  Output: xc_incoherent_single,
+//                     planar layout [batch][3][n_f][9600].
+//   sp_partial        sliding 274-sample signal power per half frame (sp_est), FP64.
+//   epilogue          delay-spread box filter (same float summation order as searcher.cpp:330-343),
+//                     strict-> first-max over f (searcher.cpp:369-382), sp fold + 137-sample shift.
+//
+// Work decomposition of xcorr_fold_fp32: a block owns 224 consecutive fold positions (idx) and 8
+// frequency hypotheses (one per warp); each lane owns 7 consecutive idx x 3 roots.  For every half
+// frame m the block stages the samples it needs into shared memory once (coalesced 128-bit loads /
+// byte loads converted in flight), then each lane slides a 7-sample register window across the
+// 137 taps: per tap 1 LDS.64 (new sample) + LDS.128 + LDS.64 (3 template taps, warp broadcast) feed
+// 21 complex MACs = 84 FFMA.  The k_factor-dependent fold offsets round_i(m*.005*k_f*fs)
+// (searcher.cpp:298) differ per hypothesis; each warp simply offsets its window into the shared
+// tile.  A 7-sample (56 B) lane stride makes the LDS.64 window loads bank-conflict free.
+#include <assert.h>
+
+#include "lcs_internal.hpp"
+
+namespace lcs {
+
+template <int FMT>
+__device__ __forceinline__ float2 load_iq(const void* __restrict__ base, size_t i);
+template <>
+__device__ __forceinline__ float2 load_iq<LCS_IQ_CF32>(const void* __restrict__ base, size_t i) {
+  return __ldg(reinterpret_cast<const float2*>(base) + i);
+}
+template <>
+__device__ __forceinline__ float2 load_iq<LCS_IQ_CU8>(const void* __restrict__ base, size_t i) {
+  // sample = (u8-127)/128, exact in fp32  (reference src/capbuf.cpp:172-175)
+  uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + i);
+  return make_float2((float)((int)v.x - 127) * 0.0078125f, (float)((int)v.y - 127) * 0.0078125f);
+}
+
+template <>
+__device__ __forceinline__ float2 load_iq<LCS_IQ_C128>(const void* __restrict__ base, size_t i) {
+  // IT++ cvec boundary format; rounded once to fp32 for the correlator
+  double2 v = __ldg(reinterpret_cast<const double2*>(base) + i);
+  return make_float2((float)v.x, (float)v.y);
+}
+
+#define LCS_DISPATCH_FMT(fmt, CALL)                      \
+  do {                                                   \
+    if ((fmt) == LCS_IQ_CU8) { CALL(LCS_IQ_CU8); }       \
+    else if ((fmt) == LCS_IQ_C128) { CALL(LCS_IQ_C128); } \
+    else { CALL(LCS_IQ_CF32); }                          \
+  } while (0)
+
+__device__ __forceinline__ void cmac(float2& acc, const float wx, const float wy, const float2 x) {
+  acc.x = fmaf(wx, x.x, acc.x);
+  acc.x = fmaf(-wy, x.y, acc.x);
+  acc.y = fmaf(wx, x.y, acc.y);
+  acc.y = fmaf(wy, x.x, acc.y);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(XC_THREADS, 2)
+xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w01g, const float2* __restrict__ w2g,
+                       const int* __restrict__ soff, const int* __restrict__ smin_tab, float* __restrict__ single_planar,
+                       const uint32_t n_cap, const uint32_t n_f, const uint32_t n_comb, const uint32_t n_fchunk,
+                       const uint32_t tile_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* w01s = reinterpret_cast<float4*>(smem_raw);                        // [FW][NTAP_PAD] roots 0,1
+  float2* w2s = reinterpret_cast<float2*>(w01s + XC_FW * XC_NTAP_PAD);       // [FW][NTAP_PAD] root 2
+  float2* tile = w2s + XC_FW * XC_NTAP_PAD;                                  // [tile_len]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t fchunk = blockIdx.y, b = blockIdx.z;
+  const uint32_t f = fchunk * XC_FW + warp;
+  const bool f_ok = f < n_f;
+  const uint32_t fcl = f_ok ? f : n_f - 1;
+  const uint32_t i0 = blockIdx.x * XC_TI;
+  const size_t iq_base = (size_t)b * n_cap;
+
+  for (int i = tid; i < XC_FW * XC_NTAP_PAD; i += XC_THREADS) {
+    const uint32_t fw = i / XC_NTAP_PAD, tap = i - fw * XC_NTAP_PAD;
+    uint32_t ff = fchunk * XC_FW + fw;
+    ff = ff < n_f ? ff : n_f - 1;
+    w01s[i] = __ldg(w01g + (size_t)ff * XC_NTAP_PAD + tap);
+    w2s[i] = __ldg(w2g + (size_t)ff * XC_NTAP_PAD + tap);
+  }
+
+  float pw[3][XC_R];
+#pragma unroll
+  for (int t = 0; t < 3; t++)
+#pragma unroll
+    for (int j = 0; j < XC_R; j++) pw[t][j] = 0.f;
+
+  const float4* w01w = w01s + warp * XC_NTAP_PAD;
+  const float2* w2w = w2s + warp * XC_NTAP_PAD;
+
+  for (uint32_t m = 0; m < n_comb; m++) {
+    const int smin = __ldg(smin_tab + m * n_fchunk + fchunk);
+    const int off = __ldg(soff + m * n_f + fcl) - smin;
+    __syncthreads();  // everyone is done with the previous tile (and, for m==0, the W stores are issued)
+    for (uint32_t e = tid; e < tile_len; e += XC_THREADS) {
+      const size_t g = (size_t)i0 + smin + e;
+      tile[e] = g < n_cap ? load_iq<FMT>(iq, iq_base + g) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    const float2* xp = tile + off + lane * XC_R;
+    float2 acc[3][XC_R];
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+      for (int j = 0; j < XC_R; j++) acc[t][j] = make_float2(0.f, 0.f);
+    float2 win[XC_R];
+#pragma unroll
+    for (int j = 0; j < XC_R - 1; j++) win[j] = xp[j];
+
+#pragma unroll 1
+    for (int tb = 0; tb < XC_NTAP_PAD; tb += XC_R) {
+#pragma unroll
+      for (int u = 0; u < XC_R; u++) {
+        win[(u + XC_R - 1) % XC_R] = xp[tb + u + XC_R - 1];
+        const float4 wa = w01w[tb + u];
+        const float2 wb = w2w[tb + u];
+#pragma unroll
+        for (int j = 0; j < XC_R; j++) {
+          const float2 x = win[(u + j) % XC_R];
+          cmac(acc[0][j], wa.x, wa.y, x);
+          cmac(acc[1][j], wa.z, wa.w, x);
+          cmac(acc[2][j], wb.x, wb.y, x);
+        }
+      }
+    }
+    // IT++ sqr(complex<float>) then float += : re*re+im*im, un-fused  (searcher.cpp:300)
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+      for (int j = 0; j < XC_R; j++)
+        pw[t][j] = __fadd_rn(pw[t][j], __fadd_rn(__fmul_rn(acc[t][j].x, acc[t][j].x), __fmul_rn(acc[t][j].y, acc[t][j].y)));
+  }
+
+  if (f_ok) {
+    const float ncf = (float)n_comb;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      float* dst = single_planar + (((size_t)b * 3 + t) * n_f + f) * LCS_N_FOLD;
+#pragma unroll
+      for (int j = 0; j < XC_R; j++) {
+        const uint32_t idx = i0 + lane * XC_R + j;
+        if (idx < LCS_N_FOLD) dst[idx] = __fdiv_rn(pw[t][j], ncf);  // searcher.cpp:304
+      }
+    }
+  }
+}
+
+int launch_xcorr_fold_fp32(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, const float4* d_w01,
+                           const float2* d_w2, const int* d_soff, const int* d_smin, float* d_single_planar,
+                           cudaStream_t st) {
+  const size_t smem = (size_t)XC_FW * XC_NTAP_PAD * (sizeof(float4) + sizeof(float2)) + (size_t)g.tile_len * sizeof(float2);
+  dim3 grid((LCS_N_FOLD + XC_TI - 1) / XC_TI, g.n_fchunk, batch), block(XC_THREADS);
+#define CALL(F)                                                                                                  \
+  cudaFuncSetAttribute(xcorr_fold_fp32_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+  xcorr_fold_fp32_kernel<F><<<grid, block, smem, st>>>(d_iq, d_w01, d_w2, d_soff, d_smin, d_single_planar, g.n_cap, \
+                                                       g.n_f, g.n_comb_xc, g.n_fchunk, g.tile_len)
+  LCS_DISPATCH_FMT(iq_format, CALL);
+#undef CALL
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// sp_est  (searcher.cpp:185-221): sp[t] = mean_{j<274} |x[t+j]|^2 for t < n_comb_sp*9600.
+// One thread = 8 consecutive t of one half frame: a 274-term sum, then 7 slides.  FP64.
+// Output sp_partial[b][m][i] (i<9600); the fold over m happens in the epilogue.
+// ------------------------------------------------------------------------------------------
+constexpr int SP_PER_THREAD = 8;
+constexpr int SP_THREADS = 128;
+
+template <int FMT>
+__device__ __forceinline__ double pwr(const void* __restrict__ iq, size_t i) {
+  if (FMT == LCS_IQ_C128) {  // keep the IT++ doubles: sp_est is an FP64 routine in the reference
+    const double2 v = __ldg(reinterpret_cast<const double2*>(iq) + i);
+    return v.x * v.x + v.y * v.y;
+  }
+  const float2 v = load_iq<FMT>(iq, i);
+  return (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(SP_THREADS) sp_partial_kernel(const void* __restrict__ iq, double* __restrict__ sp_partial,
+                                                                const uint32_t n_cap, const uint32_t n_comb_sp) {
+  const uint32_t m = blockIdx.y, b = blockIdx.z;
+  const uint32_t i_base = (blockIdx.x * SP_THREADS + threadIdx.x) * SP_PER_THREAD;
+  if (i_base >= LCS_N_FOLD) return;
+  const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
+  double s = 0;
+  for (int j = 0; j < 274; j++) s += pwr<FMT>(iq, base + j);
+  double* dst = sp_partial + ((size_t)b * n_comb_sp + m) * LCS_N_FOLD + i_base;
+  dst[0] = s / 274;
+#pragma unroll
+  for (int q = 1; q < SP_PER_THREAD; q++) {
+    if (i_base + q >= LCS_N_FOLD) break;
+    s += pwr<FMT>(iq, base + 273 + q) - pwr<FMT>(iq, base + q - 1);
+    dst[q] = s / 274;
+  }
+}
+
+int launch_sp_partial(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_partial,
+                      cudaStream_t st) {
+  dim3 grid((LCS_N_FOLD + SP_THREADS * SP_PER_THREAD - 1) / (SP_THREADS * SP_PER_THREAD), g.n_comb_sp, batch);
+#define CALL(F) sp_partial_kernel<F><<<grid, SP_THREADS, 0, st>>>(d_iq, d_sp_partial, g.n_cap, g.n_comb_sp)
+  LCS_DISPATCH_FMT(iq_format, CALL);
+#undef CALL
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Epilogue: xc_delay_spread (searcher.cpp:312-347) + xc_peak_freq (:353-383) + the sp fold and
+// tshift(sp_incoherent,137) of sp_est (:213-220).  One thread per (t, idx); planar reads are
+// coalesced along idx.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__ single_planar,
+                                                       const double* __restrict__ sp_partial, double* __restrict__ pow_out,
+                                                       int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
+                                                       float* __restrict__ incoherent_planar, const uint32_t n_f,
+                                                       const uint32_t arm, const uint32_t n_comb_sp) {
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
+  if (idx >= LCS_N_FOLD) return;
+  const float* s = single_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD;
+  float* inc_out = incoherent_planar ? incoherent_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD : nullptr;
+  const float denom = (float)(2 * arm + 1);
+  float best = 0.f;
+  int best_f = 0;
+  for (uint32_t f = 0; f < n_f; f++) {
+    const float* sf = s + (size_t)f * LCS_N_FOLD;
+    float v = sf[idx];
+    for (uint32_t a = 1; a <= arm; a++) {
+      const uint32_t lo = (idx + LCS_N_FOLD - a) % LCS_N_FOLD, hi = (idx + a) % LCS_N_FOLD;
+      v = __fadd_rn(v, __fadd_rn(sf[lo], sf[hi]));  // searcher.cpp:336: += single[idx-t]+single[idx+t]
+    }
+    v = __fdiv_rn(v, denom);  // :343
+    if (inc_out) inc_out[(size_t)f * LCS_N_FOLD + idx] = v;
+    if (f == 0 || v > best) { best = v; best_f = (int)f; }  // :371-377 strict >, first max wins
+  }
+  pow_out[((size_t)b * 3 + t) * LCS_N_FOLD + idx] = (double)best;
+  frq_out[((size_t)b * 3 + t) * LCS_N_FOLD + idx] = best_f;
+  if (t == 0) {
+    const double* sp = sp_partial + (size_t)b * n_comb_sp * LCS_N_FOLD;
+    double acc = sp[idx];
+    for (uint32_t m = 1; m < n_comb_sp; m++) acc += sp[(size_t)m * LCS_N_FOLD + idx];
+    sp_incoherent[(size_t)b * LCS_N_FOLD + (idx + 137) % LCS_N_FOLD] = acc / n_comb_sp;
+  }
+}
+
+int launch_epilogue(const XcorrGeom& g, uint32_t batch, const float* d_single_planar, const double* d_sp_partial,
+                    double* d_pow, int32_t* d_frq, double* d_sp_incoherent, float* d_incoherent_planar,
+                    cudaStream_t st) {
+  dim3 grid((LCS_N_FOLD + 255) / 256, 3, batch);
+  epilogue_kernel<<<grid, 256, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent,
+                                        d_incoherent_planar, g.n_f, g.ds_comb_arm, g.n_comb_sp);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout / format helpers for the drop-in host call.
+// ------------------------------------------------------------------------------------------
+// planar [3][n_f][9600] -> ref vf3d [3][9600][n_f]; 32x32 shared-memory transpose.
+__global__ void planar_to_ref_kernel(const float* __restrict__ planar, float* __restrict__ ref, const uint32_t n_f) {
+  __shared__ float tilebuf[32][33];
+  const uint32_t t = blockIdx.z, i0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const uint32_t f = f0 + r, i = i0 + threadIdx.x;
+    tilebuf[r][threadIdx.x] = (f < n_f && i < LCS_N_FOLD) ? planar[((size_t)t * n_f + f) * LCS_N_FOLD + i] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const uint32_t i = i0 + r, f = f0 + threadIdx.x;
+    if (f < n_f && i < LCS_N_FOLD) ref[((size_t)t * LCS_N_FOLD + i) * n_f + f] = tilebuf[threadIdx.x][r];
+  }
+}
+int launch_planar_to_ref(const XcorrGeom& g, const float* d_planar, float* d_ref, cudaStream_t st) {
+  dim3 grid((LCS_N_FOLD + 31) / 32, (g.n_f + 31) / 32, 3), block(32, 8);
+  planar_to_ref_kernel<<<grid, block, 0, st>>>(d_planar, d_ref, g.n_f);
+  return 1;
+}
+
+// Debug-only materialisation of xc (searcher.h:37, vcf3d [t][k][f]) with the same FP32 arithmetic
+// order as the fused kernel; one thread per (k, f).
+template <int FMT>
+__global__ void __launch_bounds__(128) xc_debug_kernel(const void* __restrict__ iq, const float4* __restrict__ w01g,
+                                                       const float2* __restrict__ w2g, float2* __restrict__ xc,
+                                                       const uint32_t n_cap, const uint32_t n_f) {
+  const uint32_t n_lag = n_cap - 136;
+  const uint32_t k = blockIdx.x * 128 + threadIdx.x, f = blockIdx.y;
+  if (k >= n_lag) return;
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+  for (int m = 0; m < LCS_N_TAPS; m++) {
+    const float2 x = load_iq<FMT>(iq, (size_t)k + m);
+    const float4 wa = __ldg(w01g + (size_t)f * XC_NTAP_PAD + m);
+    const float2 wb = __ldg(w2g + (size_t)f * XC_NTAP_PAD + m);
+    cmac(a0, wa.x, wa.y, x);
+    cmac(a1, wa.z, wa.w, x);
+    cmac(a2, wb.x, wb.y, x);
+  }
+  xc[((size_t)0 * n_lag + k) * n_f + f] = a0;
+  xc[((size_t)1 * n_lag + k) * n_f + f] = a1;
+  xc[((size_t)2 * n_lag + k) * n_f + f] = a2;
+}
+int launch_xc_debug(const XcorrGeom& g, const void* d_iq, int iq_format, const float4* d_w01, const float2* d_w2,
+                    float2* d_xc, cudaStream_t st) {
+  dim3 grid((g.n_cap - 136 + 127) / 128, g.n_f);
+#define CALL(F) xc_debug_kernel<F><<<grid, 128, 0, st>>>(d_iq, d_w01, d_w2, d_xc, g.n_cap, g.n_f)
+  LCS_DISPATCH_FMT(iq_format, CALL);
+#undef CALL
+  return 1;
+}
+
+// Debug-only `sp` (searcher.h:38): [n_comb_sp*9600] doubles.
+template <int FMT>
+__global__ void sp_debug_kernel(const void* __restrict__ iq, double* __restrict__ sp, const uint32_t n_sp) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_sp) return;
+  double s = 0;
+  for (int j = 0; j < 274; j++) s += pwr<FMT>(iq, (size_t)t + j);
+  sp[t] = s / 274;
+}
+int launch_sp_debug(const XcorrGeom& g, const void* d_iq, int iq_format, double* d_sp, cudaStream_t st) {
+  const uint32_t n_sp = g.n_comb_sp * LCS_N_FOLD;
+#define CALL(F) sp_debug_kernel<F><<<(n_sp + 255) / 256, 256, 0, st>>>(d_iq, d_sp, n_sp)
+  LCS_DISPATCH_FMT(iq_format, CALL);
+#undef CALL
+  return 1;
+}
+
+}  // namespace lcs

@@ -1,0 +1,199 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances: correlation magnitudes |a-b| <= 1e-6*max|ref| per array;
+cell ids, peak indices, frequency indices at detections and MIB fields bit-exact; FP64 companion
+stages (sss_detect, pss_sss_foe, extract_tfg) to 1e-9 relative or better."""
+import numpy as np
+import pytest
+
+from conftest import cu8_to_c128, load, synth_cu8
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def rel_err(a, ref):
+    return np.abs(np.asarray(a, np.float64) - ref).max() / np.abs(ref).max()
+
+
+def frq_mismatch_is_near_tie(frq_gpu, ref, tol=4e-6):
+    """argmax over f may differ only where the two best hypotheses are within fp32 noise."""
+    bad = np.argwhere(frq_gpu != ref["frq"])
+    for t, k in bad:
+        v = ref["incoherent"][t, k]
+        if abs(v[frq_gpu[t, k]] - v[ref["frq"][t, k]]) > tol * ref["incoherent"].max():
+            return False
+    return len(bad) < 0.002 * frq_gpu.size
+
+
+def check_xcorr(out, ref):
+    assert out["n_comb_xc"] == ref["n_comb_xc"] and out["n_comb_sp"] == ref["n_comb_sp"]
+    assert rel_err(out["single"], ref["single"]) < REL
+    assert rel_err(out["incoherent"], ref["incoherent"]) < REL
+    assert rel_err(out["pow"], ref["pow"]) < REL
+    assert np.abs(out["sp_incoherent"] / ref["sp_incoherent"] - 1).max() < 1e-12
+    assert frq_mismatch_is_near_tie(out["frq"], ref)
+
+
+def test_xcorr_pss_dropin_capbuf_0000(ctx, oracle, capbuf0000):
+    """searcher.h xcorr_pss drop-in, real capture, default ppm=120 grid (n_f=37)."""
+    fc = capbuf0000["fc"]
+    f = oracle.f_search_set(fc, 120.0)
+    ref = oracle.xcorr_pss(capbuf0000["capbuf"], f, 2, fc, fc, 1.92e6)
+    out = ctx.xcorr_pss(capbuf0000["capbuf"], f, 2, fc, fc, 1.92e6)
+    check_xcorr(out, ref)
+    # the detections are decided on exactly equal indices
+    for (t, k) in [(1, 1410), (1, 6990), (2, 1314), (0, 1327)]:
+        for d in range(-2, 3):
+            assert out["frq"][t, k + d] == ref["frq"][t, k + d]
+
+
+def test_xcorr_pss_dropin_debug_outputs(ctx, oracle):
+    """xc and sp debug outputs on the reference's test_xcorr_pss capture (n_f=3)."""
+    g = load("ref_xcorr_pss.npz")
+    f = g["f_search_set"].astype(float); fc = float(g["fc"][0])
+    ref = oracle.xcorr_pss(g["capbuf"], f, 2, fc, fc, 1.92e6, want_xc=True)
+    out = ctx.xcorr_pss(g["capbuf"], f, 2, fc, fc, 1.92e6, want_xc=True, want_sp=True)
+    check_xcorr(out, ref)
+    assert np.abs(out["xc"].astype(np.complex128) - ref["xc"]).max() < REL * np.abs(ref["xc"]).max()
+    assert np.abs(out["sp"] / ref["sp"] - 1).max() < 1e-11
+
+
+@pytest.mark.parametrize("fmt", ["cu8", "cf32", "c128"])
+def test_xcorr_batch_host_formats(ctx, lcs, oracle, fmt):
+    """Batched host entry point with the three wire formats, synthetic 8-bit IQ, 2 buffers."""
+    fc = 739e6
+    f = oracle.f_search_set(fc, 20.0)          # n_f = 7 keeps the oracle fast
+    cu8 = np.stack([synth_cu8(0xC0FFEE + i) for i in range(2)])
+    plan = ctx.plan(153600, f, 2, fc, fc, 1.92e6, max_batch=2)
+    if fmt == "cu8":
+        out = plan.run_host_np(cu8, lcs.IQ_CU8)
+    elif fmt == "cf32":
+        x = ((cu8.astype(np.float32) - 127) / 128)
+        out = plan.run_host_np(x, lcs.IQ_CF32)
+    else:
+        x = ((cu8.astype(np.float64) - 127) / 128)
+        out = plan.run_host_np(x, lcs.IQ_C128)
+    for b in range(2):
+        ref = oracle.xcorr_pss(cu8_to_c128(cu8[b]), f, 2, fc, fc, 1.92e6)
+        assert rel_err(out["single"][b].transpose(0, 2, 1), ref["single"]) < REL
+        assert rel_err(out["pow"][b], ref["pow"]) < REL
+        assert np.abs(out["sp_incoherent"][b] / ref["sp_incoherent"] - 1).max() < 1e-12
+        assert frq_mismatch_is_near_tie(out["frq"][b], ref)
+    plan.close()
+
+
+def test_xcorr_edge_shapes(ctx, lcs, oracle):
+    """Ragged grids and sizes: n_f=1 (tracker mode), n_f not a multiple of 8, asymmetric offsets,
+    fc_programmed != fc_requested, short buffer (n_comb=2), arm=0."""
+    rng = np.random.default_rng(3)
+    cases = [
+        (153600, np.array([35000.0]), 2, 739e6, 739e6, 1.92e6),
+        (60000, np.arange(-4, 5) * 5000.0, 2, 739e6, 739.003e6, 1.92e6 * 1.00002),
+        (29000, np.array([-20000.0, 0.0, 5000.0]), 0, 2.1e9, 2.1e9, 1.92e6),
+        (153600, np.arange(-5, 6) * 7000.0 + 1234.5, 3, 451e6, 451e6, 1.92e6),
+    ]
+    for n_cap, f, arm, fcr, fcp, fs in cases:
+        cap = (rng.standard_normal(n_cap) + 1j * rng.standard_normal(n_cap)) * 0.2
+        ref = oracle.xcorr_pss(cap, f, arm, fcr, fcp, fs)
+        out = ctx.xcorr_pss(cap, f, arm, fcr, fcp, fs)
+        check_xcorr(out, ref)
+
+
+def test_xcorr_argument_errors(ctx, lcs):
+    with pytest.raises(lcs.LcsError):
+        ctx.plan(5000, np.array([0.0]), 2, 739e6, 739e6, 1.92e6)           # shorter than a half frame
+    with pytest.raises(lcs.LcsError):
+        ctx.plan(153600, np.array([]), 2, 739e6, 739e6, 1.92e6)            # empty grid
+    with pytest.raises(lcs.LcsError):
+        ctx.plan(153600, np.array([0.0]), 2, 739e6, 700e6, 1.92e6)         # k_factor pushes the fold out of range
+
+
+def test_xcorr_full_size_properties(ctx, lcs):
+    """BASELINE config 2 size (n_f=31, batch 4): properties that need no oracle.
+    - shift: delaying the buffer by d samples (d < 100) rotates the fold by d
+    - scaling the 8-bit amplitude about 127 by 2 scales powers by 4 (exact in fp32)
+    - batch entries are independent of their neighbours (same input -> bit-identical output)."""
+    fc = 739e6
+    f = lcs.f_search_set(fc, 100.0)
+    assert f.size == 31
+    base = synth_cu8(0xC0FFEE, sigma=10.0)
+    d = 37
+    shifted = np.roll(base, d, axis=0)
+    doubled = np.clip((base.astype(np.int32) - 127) * 2 + 127, 0, 255).astype(np.uint8)
+    assert np.array_equal((doubled.astype(np.int32) - 127), (base.astype(np.int32) - 127) * 2)
+    plan = ctx.plan(153600, f, 2, fc, fc, 1.92e6, max_batch=4)
+    out = plan.run_host_np(np.stack([base, shifted, doubled, base]), lcs.IQ_CU8)
+    s = out["single"]
+    assert np.array_equal(s[0], s[3]) and np.array_equal(out["frq"][0], out["frq"][3])
+    assert np.array_equal(s[2], s[0] * 4.0)
+    # the roll moves every lag by d except those touching the wrapped head/tail of the buffer
+    a, b = s[0][:, :, : 9600 - d], s[1][:, :, d:]
+    assert np.abs(a[:, :, 300:] - b[:, :, 300:]).max() <= 2e-6 * a.max()
+    assert out["pow"].shape == (4, 3, 9600) and (out["frq"] >= 0).all() and (out["frq"] < 31).all()
+    plan.close()
+
+
+def test_sss_detect_foe_parity(ctx, oracle):
+    """sss_detect + pss_sss_foe on the reference's synthetic capture: 24 peaks incl. 2 rejections."""
+    g = load("ref_sss_detect.npz")
+    cap = g["capbuf"]; fc = float(g["fc"][0]); th = float(g["thresh2_n_sigma"][0])
+    for t in range(len(g["peaks_pow"])):
+        kw = dict(pss_pow=g["peaks_pow"][t], ind=int(g["peaks_ind"][t]) - 1, freq=float(g["peaks_freq"][t]),
+                  n_id_2=int(g["peaks_n_id_2"][t]))
+        import lcs_b200
+        o_out, o_d = oracle.sss_detect(oracle.new_cell(**kw), cap, th, fc, fc, 1.92e6)
+        p_out, p_d = ctx.sss_detect(lcs_b200.new_cell(**kw), cap, th, fc, fc, 1.92e6)
+        for k in ["h1_np", "h2_np", "h1_nrm", "h2_nrm", "h1_ext", "h2_ext"]:
+            assert np.abs(p_d[k] - o_d[k]).max() < 1e-10 * max(1.0, np.abs(o_d[k]).max())
+        assert np.abs(p_d["log_lik_nrm"] - o_d["log_lik_nrm"]).max() < 1e-8 * np.abs(o_d["log_lik_nrm"]).max()
+        assert np.abs(p_d["log_lik_ext"] - o_d["log_lik_ext"]).max() < 1e-8 * np.abs(o_d["log_lik_ext"]).max()
+        assert (p_out.n_id_1, p_out.cp_type) == (o_out.n_id_1, o_out.cp_type)
+        if o_out.n_id_1 >= 0:
+            assert abs(p_out.frame_start - o_out.frame_start) < 1e-9
+            o2 = oracle.pss_sss_foe(o_out, cap, fc, fc, 1.92e6)
+            p2 = ctx.pss_sss_foe(p_out, cap, fc, fc, 1.92e6)
+            assert abs(p2.freq_fine - o2.freq_fine) < 1e-6
+        else:
+            assert np.isnan(p_out.frame_start)
+    # golden decisions (mode independent): ids and CP types of test_sss_detect.it
+    n1 = g["peaks_out_n_id_1"]
+    assert np.isnan(n1).sum() == 2
+
+
+def test_extract_tfg_parity(ctx, oracle, lcs):
+    g = load("ref_tfg.npz")
+    cap = g["capbuf"]; fc = float(g["fc"][0])
+    kw = dict(n_id_1=92, n_id_2=1, cp_type=1, frame_start=float(g["peaks_in_frame_start"][0]) - 1,
+              freq_fine=float(g["peaks_in_freq_fine"][0]))
+    o_tfg, o_ts = oracle.extract_tfg(oracle.new_cell(**kw), cap, fc, fc, 1.92e6)
+    p_tfg, p_ts = ctx.extract_tfg(lcs.new_cell(**kw), cap, fc, fc, 1.92e6)
+    assert p_tfg.shape == (854, 72) and np.array_equal(p_ts, o_ts)
+    assert np.abs(p_tfg - o_tfg).max() < 1e-11 * np.abs(o_tfg).max()
+    kw["cp_type"] = 2                                   # extended CP: 732 symbols
+    o_tfg, o_ts = oracle.extract_tfg(oracle.new_cell(**kw), cap, fc, fc, 1.92e6)
+    p_tfg, p_ts = ctx.extract_tfg(lcs.new_cell(**kw), cap, fc, fc, 1.92e6)
+    assert p_tfg.shape == (732, 72) and np.abs(p_tfg - o_tfg).max() < 1e-11 * np.abs(o_tfg).max()
+    with pytest.raises(lcs.LcsError):
+        ctx.extract_tfg(lcs.new_cell(n_id_1=92, n_id_2=1), cap, fc, fc, 1.92e6)     # cp_type unknown
+
+
+@pytest.mark.parametrize("fmt", ["c128", "cu8"])
+def test_full_chain_capbuf_0000(ctx, oracle, capbuf0000, fmt):
+    """BASELINE config 3: xcorr_pss -> peak_search -> sss_detect -> pss_sss_foe -> extract_tfg -> tfoec ->
+    decode_mib on the shipped real capture; ids / MIB bit-exact vs the oracle, cells 277 and 271."""
+    fc = capbuf0000["fc"]
+    f = oracle.f_search_set(fc, 120.0)
+    o_cells, o_peaks = oracle.cell_search_one(capbuf0000["capbuf"], f, fc, fc, 1.92e6)
+    cap = capbuf0000["capbuf"] if fmt == "c128" else capbuf0000["cu8"]
+    p_cells, p_peaks = ctx.cell_search(cap, f, fc, fc, 1.92e6)
+    assert [(p.n_id_2, p.ind, p.freq) for p in p_peaks] == [(p.n_id_2, p.ind, p.freq) for p in o_peaks]
+    for a, b in zip(p_peaks, o_peaks):
+        assert abs(a.pss_pow - b.pss_pow) < REL * o_peaks[0].pss_pow
+    assert [c.n_id_cell() for c in p_cells] == [277, 271] == [c.n_id_cell() for c in o_cells]
+    for a, b in zip(p_cells, o_cells):
+        for k in ("n_id_1", "n_id_2", "cp_type", "ind", "n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"):
+            assert getattr(a, k) == getattr(b, k), k
+        assert abs(a.frame_start - b.frame_start) < 1e-9
+        assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6

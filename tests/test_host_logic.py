@@ -1,0 +1,120 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol that
+include/lcs_b200.h declares, fails loudly without a GPU, and its host stages (threshold,
+peak_search, tfoec, decode_mib, dedup) agree with the oracle and with the reference's goldens."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import has_gpu, load
+
+
+def test_library_exports_every_declared_symbol(lcs):
+    l = lcs.lib()
+    names = lcs.declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(l, n)]
+    assert not missing, missing
+    assert b"sm_100a" in l.lcs_version()
+    assert C.sizeof(lcs.Cell) == 104
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lcs):
+    with pytest.raises(lcs.LcsError, match="no CUDA device"):
+        lcs.Context(0)
+
+
+def test_f_search_set_matches_reference_formula(lcs, oracle):
+    for fc, ppm in [(739e6, 120.0), (739e6, 100.0), (715e6, 120.0), (768e6, 120.0), (2.6e9, 20.0)]:
+        a, b = lcs.f_search_set(fc, ppm), oracle.f_search_set(fc, ppm)
+        assert np.array_equal(a, b)
+    assert lcs.f_search_set(739e6, 100.0).size == 31 and lcs.f_search_set(739e6, 120.0).size == 37
+
+
+def test_z_th1_matches_oracle(lcs, oracle):
+    rng = np.random.default_rng(0)
+    spi = 0.05 + 0.01 * rng.random(9600)
+    for n_comb, arm in [(15, 2), (14, 2), (15, 0)]:
+        a, b = lcs.calc_z_th1(spi, n_comb, arm), oracle.calc_Z_th1(spi, n_comb, arm) if arm == 2 or True else None
+        assert np.abs(a / b - 1).max() < 1e-12
+
+
+def test_peak_search_golden(lcs):
+    g = load("ref_peak_search.npz")
+    pw = g["xc_incoherent_collapsed_pow"]; frq = g["xc_incoherent_collapsed_frq"] - 1
+    f = g["f_search_set"].astype(float)
+    single = np.repeat(pw[:, None, :], f.size, axis=1).astype(np.float32)     # planar [3][n_f][9600]
+    cells = lcs.peak_search(pw, frq, g["Z_th1"], f, 739e6, 739e6, single, 0)
+    assert len(cells) == 20
+    for c, p, i, fr, n in zip(cells, g["peaks_pow"], g["peaks_ind"], g["peaks_freq"], g["peaks_n_id_2"]):
+        assert abs(c.pss_pow - p) < 1e-6 and c.ind == i - 1 and c.freq == fr and c.n_id_2 == n
+
+
+def test_peak_search_matches_oracle_random(lcs, oracle):
+    rng = np.random.default_rng(5)
+    n_f = 5
+    f = np.arange(-2, 3) * 5000.0
+    for trial in range(4):
+        single = rng.random((3, n_f, 9600)).astype(np.float32) * 0.01
+        for _ in range(6):                                    # plant peaks, some at the wrap-around edges
+            t, fi = rng.integers(0, 3), rng.integers(0, n_f)
+            idx = [0, 1, 9599, 4000, 7000, 9598][_] if trial == 0 else rng.integers(0, 9600)
+            single[t, fi, idx] += rng.random() * 2 + 0.5
+        inc = single.astype(np.float64)
+        pw = inc.max(axis=1); frq = inc.argmax(axis=1).astype(np.int32)
+        z = np.full(9600, 0.3)
+        a = lcs.peak_search(pw, frq, z, f, 739e6, 739.01e6, single, 2)
+        b = oracle.peak_search(pw, frq, z, f, 739e6, 739.01e6, single.transpose(0, 2, 1).astype(np.float64), 2)
+        assert len(a) == len(b) and len(a) > 0
+        for x, y in zip(a, b):
+            assert (x.ind, x.freq, x.n_id_2, x.pss_pow, x.fc_programmed) == (y.ind, y.freq, y.n_id_2, y.pss_pow, y.fc_programmed)
+
+
+def _golden_tfg_cell(m):
+    return m.new_cell(n_id_1=92, n_id_2=1, cp_type=1, frame_start=17448.5250338295, freq_fine=39684.07746316391)
+
+
+def test_tfoec_and_decode_mib_match_oracle(lcs, oracle):
+    """Product host stages vs the oracle (HEAD semantics) on the golden TFG of cell 277."""
+    g = load("ref_tfg.npz")
+    fc = float(g["fc"][0])
+    o_cell, o_tc, o_ts = oracle.tfoec(_golden_tfg_cell(oracle), g["tfg"], g["tfg_timestamp"] - 1, fc, fc)
+    p_cell, p_tc, p_ts = lcs.tfoec(_golden_tfg_cell(lcs), g["tfg"], g["tfg_timestamp"] - 1, fc, fc)
+    assert np.abs(p_tc - o_tc).max() < 1e-11 and np.abs(p_ts - o_ts).max() < 1e-9
+    assert abs(p_cell.freq_superfine - o_cell.freq_superfine) < 1e-7
+    o_m, dbg = oracle.decode_mib(o_cell, o_tc)
+    p_m = lcs.decode_mib(p_cell, p_tc)
+    for k in ("n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"):
+        assert getattr(p_m, k) == getattr(o_m, k)
+    assert (p_m.n_ports, p_m.n_rb_dl, p_m.sfn) == (2, 50, 649)
+
+
+def test_decode_mib_kat(lcs):
+    """Bit-exact KAT on the reference's stored tfg_comp (test/test_tfg.it)."""
+    g = load("ref_tfg.npz")
+    m = lcs.decode_mib(lcs.new_cell(n_id_1=92, n_id_2=1, cp_type=1), g["tfg_comp"])
+    assert (m.n_ports, m.n_rb_dl, m.phich_duration, m.phich_resource, m.sfn) == (2, 50, 1, 3, 649)
+    # a wrong cell id must not decode (CRC + scrambling)
+    m2 = lcs.decode_mib(lcs.new_cell(n_id_1=91, n_id_2=1, cp_type=1), g["tfg_comp"])
+    assert m2.n_rb_dl == -1 and m2.n_ports == -1
+
+
+def test_chan_est_noise_and_errors(lcs):
+    g = load("ref_tfg.npz")
+    with pytest.raises(lcs.LcsError):
+        lcs.decode_mib(lcs.new_cell(n_id_1=92, n_id_2=1, cp_type=0), g["tfg_comp"])        # cp_type unknown
+    with pytest.raises(lcs.LcsError):
+        lcs.decode_mib(lcs.new_cell(n_id_1=92, n_id_2=1, cp_type=1), g["tfg_comp"][:100])  # grid too short
+
+
+def test_dedup_matches_oracle(lcs, oracle):
+    def mk(m, cid, fc, sf, pw):
+        return m.new_cell(n_id_1=cid // 3, n_id_2=cid % 3, fc_requested=fc, freq_superfine=sf, pss_pow=pw)
+    spec = [(277, 739e6, 35e3, 0.06), (271, 739e6, 35e3, 0.016), (277, 739.1e6, -65e3, 0.08),
+            (277, 741e6, 0.0, 0.01), (271, 739.1e6, -65e3, 0.001)]
+    a = lcs.dedup([mk(lcs, *s) for s in spec])
+    b = oracle.dedup([mk(oracle, *s) for s in spec])
+    assert [(c.n_id_cell(), c.fc_requested, c.pss_pow) for c in a] == [(c.n_id_cell(), c.fc_requested, c.pss_pow) for c in b]
+    assert [(c.n_id_cell(), c.fc_requested) for c in a] == [(277, 739.1e6), (271, 739e6), (277, 741e6)]
+    assert lcs.dedup([]) == []
