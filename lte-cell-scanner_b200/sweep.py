@@ -1,0 +1,79 @@
+"""Multi-GPU frequency sweep: the per-centre-frequency loop of CellSearch (reference
+src/CellSearch.cpp:471-569) sharded over the ranks of one node.
+
+Centre frequencies (one capture buffer each) are independent (CellSearch.cpp:467-469), so rank r
+takes channels r, r+W, r+2W, ... and runs the whole chain for each on its own GPU - no data-path
+collective.  The only exchange is the final gather of the fixed-size detected-cell records to
+rank 0, which applies the reference's cross-frequency `dedup` (CellSearch.cpp:285-319; it needs
+all cells).  With torch.distributed this is one all_gather of a padded [max_cells, 16] float64
+tensor per rank (NCCL over NVLink on GPUs, gloo on CPU in the tests).
+"""
+import numpy as np
+
+CELL_FIELDS = ["fc_requested", "fc_programmed", "pss_pow", "ind", "freq", "n_id_2", "n_id_1", "cp_type", "frame_start",
+               "freq_fine", "freq_superfine", "n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"]
+
+
+def shard(n_items, rank, world):
+    """Round-robin assignment of channel indices (BASELINE config 4)."""
+    return list(range(rank, n_items, world))
+
+
+def cells_to_array(cells, max_cells):
+    """Pack cells (objects with the lcs_cell fields) into a fixed [max_cells+1, 16] float64 array;
+    row 0 holds the count.  Every field of lcs_cell is exactly representable in float64."""
+    a = np.full((max_cells + 1, len(CELL_FIELDS)), np.nan)
+    n = min(len(cells), max_cells)
+    a[0, 0] = n
+    for i in range(n):
+        for j, k in enumerate(CELL_FIELDS):
+            a[i + 1, j] = getattr(cells[i], k)
+    return a
+
+
+def array_to_cells(a, new_cell):
+    out = []
+    int_fields = {"ind", "n_id_2", "n_id_1", "cp_type", "n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"}
+    for i in range(int(a[0, 0])):
+        kw = {}
+        for j, k in enumerate(CELL_FIELDS):
+            v = a[i + 1, j]
+            kw[k] = int(v) if k in int_fields else float(v)
+        out.append(new_cell(**kw))
+    return out
+
+
+def sweep(channels, search_fn, new_cell, dedup_fn, dist=None, device=None, max_cells_per_rank=256):
+    """channels: list of (channel_index, fc_requested, capbuf).  search_fn(fc, capbuf) -> list of cells.
+    Returns the deduplicated list on rank 0 (None elsewhere).  `dist` is torch.distributed (initialised)
+    or None for a single process."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    mine = []           # (channel index, cells) in channel order
+    for pos in shard(len(channels), rank, world):
+        idx, fc, cap = channels[pos]
+        mine.append((idx, search_fn(fc, cap)))
+    flat = [c for _, cs in mine for c in cs]
+    order = [idx for idx, cs in mine for _ in cs]
+    if dist is None:
+        return dedup_fn(flat)
+    import torch
+    arr = cells_to_array(flat, max_cells_per_rank)
+    tag = np.full((max_cells_per_rank + 1, 1), -1.0)
+    tag[1:1 + len(order), 0] = order[:max_cells_per_rank]
+    t = torch.from_numpy(np.concatenate([arr, tag], axis=1))
+    if device is not None:
+        t = t.to(device)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    if rank != 0:
+        return None
+    tagged = []
+    for g in gathered:
+        g = g.cpu().numpy()
+        cs = array_to_cells(g[:, :-1], new_cell)
+        tagged += list(zip(g[1:1 + len(cs), -1].astype(int), cs))
+    # restore the reference's visiting order (ascending centre frequency) before dedup: the result of
+    # dedup depends on the order in which equal-power candidates are met
+    tagged.sort(key=lambda x: x[0])
+    return dedup_fn([c for _, c in tagged])

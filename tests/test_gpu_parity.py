@@ -107,7 +107,7 @@ def test_xcorr_argument_errors(ctx, lcs):
     with pytest.raises(lcs.LcsError):
         ctx.plan(153600, np.array([]), 2, 739e6, 739e6, 1.92e6)            # empty grid
     with pytest.raises(lcs.LcsError):
-        ctx.plan(153600, np.array([0.0]), 2, 739e6, 700e6, 1.92e6)         # k_factor pushes the fold out of range
+        ctx.plan(20000, np.array([0.0]), 2, 739e6, 600e6, 1.92e6)          # k_factor pushes the fold out of range
 
 
 def test_xcorr_full_size_properties(ctx, lcs):
@@ -197,3 +197,32 @@ def test_full_chain_capbuf_0000(ctx, oracle, capbuf0000, fmt):
             assert getattr(a, k) == getattr(b, k), k
         assert abs(a.frame_start - b.frame_start) < 1e-9
         assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6
+
+
+def test_cellsearch_cli_full_test(tmp_path, capbuf0000):
+    """The reference's (commented-out) integration test, src/CMakeLists.txt:34-35:
+    `CellSearch -s 739000000 -l -d test` must print `cell ID: 271`.  Run through the C++ drop-in
+    (searcher.h mirror + CLI) on a capbuf_0000.it regenerated from the committed fixture."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from itfile import write_it
+    host = os.path.join(root, "lte-cell-scanner_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    write_it(str(tmp_path / "capbuf_0000.it"), {"capbuf": capbuf0000["capbuf"], "fc": np.array([739000000], np.int32)})
+    out = subprocess.run([os.path.join(host, "CellSearch_b200"), "-s", "739000000", "-l", "-d", str(tmp_path)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert re.search(r"cell.ID..271", out.stdout) and re.search(r"cell.ID..277", out.stdout)
+    rows = [l for l in out.stdout.splitlines() if re.match(r"^\s*27[17]\s+2\s", l)]
+    assert len(rows) == 2
+    for r in rows:                      # CID A fc foff RXPWR C nRB P PR ...  (doc/CellSearch.html example)
+        assert " N  50 N one " in r and "739M" in r
+    # raw rtl_sdr byte dump path
+    capbuf0000["cu8"].tofile(str(tmp_path / "capbuf_0000.bin"))
+    out2 = subprocess.run([os.path.join(host, "CellSearch_b200"), "-s", "739000000", "-l", "--raw", "-b", "-d", str(tmp_path)],
+                          capture_output=True, text=True, timeout=300)
+    assert out2.returncode == 0 and len([l for l in out2.stdout.splitlines() if re.match(r"^\s*27[17]\s+2\s", l)]) == 2
