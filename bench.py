@@ -105,6 +105,32 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(self.rows))
 
 
+def host_threads():
+    """Threads the CPU arm may use: physical cores visible to this process (affinity mask, cgroup quota).
+    Hyper-threads only add barrier contention to the 93 OpenMP regions per capture buffer."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    try:
+        cores = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+                cores.add((phys, core))
+        if cores:
+            n = min(n, len(cores))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def run_reference(args):
     """--impl reference: the CPU oracle (HEAD-faithful port of searcher.cpp:113-383, OpenMP over
     the lag index like searcher.cpp:153) on this box's host cores.  The reference binary itself
@@ -115,7 +141,8 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lcs_oracle as O
     f = f_grid()
-    cores = O.max_threads()
+    cores = host_threads()
+    O.set_threads(cores)
     caps = [((synth_cu8(SEED0 + i).astype(np.float64) - 127) / 128).view(np.complex128).reshape(-1) for i in range(2)]
     per_step = 1                                   # bounded sample: one capture buffer per step
     for w in range(args.warmup):
@@ -144,7 +171,8 @@ def run_reference(args):
 def cpu_baseline_leg(f, budget_s=12.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lcs_oracle as O
-    cores = O.max_threads()
+    cores = host_threads()
+    O.set_threads(cores)
     cap = ((synth_cu8(SEED0).astype(np.float64) - 127) / 128).view(np.complex128).reshape(-1)
     O.xcorr_pss(cap, f, ARM, FC, FC, FS, want_sp=False)           # warm (tables, threads)
     n, t0 = 0, time.perf_counter()

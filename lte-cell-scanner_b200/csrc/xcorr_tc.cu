@@ -1,11 +1,390 @@
-// xcorr_tc.cu - tensor-core (tcgen05) correlator for 8-bit IQ.  Placeholder until the kernel lands:
-// plans report tc_ready=false and LCS_KERNEL_AUTO resolves to the FP32 kernel.
+// xcorr_tc.cu - PSS correlator on the 5th-generation tensor cores (tcgen05 / TMEM), exact for 8-bit IQ.
+//
+// The sliding correlation is a Toeplitz GEMM: D[template, lag] = sum_j A[template, j] * z[2*lag + j],
+// j = 0..273 over the interleaved I/Q byte stream z of the capture buffer (rtl-sdr wire format,
+// reference src/capbuf.cpp:157-181).  Everything is done in EXACT integer arithmetic:
+//
+//   * IQ bytes v are used as signed x' = v-128 (a XOR with 0x80; the true sample is (x'+1)/128),
+//   * each template component W (double, conj(fshift(pss_td))/137 of searcher.cpp:145-151) is scaled by
+//     a power of two S and rounded to a 24-bit integer, split into three balanced base-256 digits
+//     W*S = 65536 a0 + 256 a1 + a2, a_j in [-128,127] -> three int8 A operands,
+//   * tcgen05.mma kind::i8 (s8 x s8 -> s32 accumulators in TMEM): |sum| <= 274*128*128 < 2^23, no overflow,
+//   * real part uses the byte stream as is, the imaginary part a second stream with every (I,Q) pair
+//     replaced by (Q, ~I)  (~I = -I'-1): sum a[2m]*Q' + a[2m+1]*(-I'-1) with the same A rows
+//     a[2m] = Re W, a[2m+1] = -Im W.
+//
+// The Toeplitz operand is never materialised per lag: an "expanded" tile P[u][r][16 B] = z[16u+2r ..+15]
+// is built once per 192-lag tile in shared memory (16x expansion of ~0.7 KB); block u is exactly the
+// 8-row x 16-byte K-major core matrix of (row group g, K chunk c) for every g+c = u, so one UMMA
+// shared-memory descriptor with LBO = SBO = 128 B addresses the whole Hankel tile.
+//
+// Per CTA (persistent, one per SM): warp 0 builds P tiles, warp 1 issues the MMAs (one elected
+// thread, 54 UTCIMMA per 32-lag sub-tile into a double-buffered set of 6 TMEM accumulators), warps
+// 2-5 read the accumulators back (tcgen05.ld), turn them into |xc|^2 and fold the 15 half frames
+// into per-template accumulators in shared memory with each template's own k_factor offset
+// (searcher.cpp:298).  Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
+#include <cstring>
+#include <cmath>
+
 #include "lcs_ctx.hpp"
 
 namespace lcs {
+
+namespace tc {
+constexpr int NT = 192;            // lags per tile
+constexpr int NSUB = NT / 32;      // 32-lag MMA sub-tiles per tile
+constexpr int KB = 288;            // K in bytes: 274 interleaved I/Q taps padded to a multiple of 32
+constexpr int KSTEPS = KB / 32;    // UTCIMMA K = 32 bytes
+constexpr int NBLK = NT / 8 + KB / 16 - 1;   // 41 expanded blocks of 128 B per tile
+constexpr int P_BYTES = NBLK * 128;          // one variant of one stage
+constexpr int A_TILE_BYTES = 128 * KB;       // one digit plane: 128 rows x 288 B = 36864
+constexpr int A_BYTES = 3 * A_TILE_BYTES;
+constexpr int T_MAX = 168;         // fold positions per tile (<= NT - max_spread)
+constexpr int POW_STRIDE = T_MAX + 1;
+constexpr int THREADS = 192;
+constexpr int SMEM_A = 0;
+constexpr int SMEM_P = SMEM_A + A_BYTES;                       // [2 stages][2 variants][P_BYTES]
+constexpr int SMEM_POW = SMEM_P + 4 * P_BYTES;                 // [128][POW_STRIDE] float
+constexpr int SMEM_BAR = SMEM_POW + 128 * POW_STRIDE * 4;      // 8 mbarriers
+constexpr int SMEM_MISC = SMEM_BAR + 8 * 8;
+constexpr int SMEM_TOTAL = SMEM_MISC + 16;
+constexpr uint32_t TMEM_COLS = 512;
+// UTCIMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) bits[4,6);
+// a_format / b_format = 1 (signed 8 bit) bits [7,10) / [10,13); K-major A and B; N>>3 bits [17,23); M>>4 bits [24,29)
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+}  // namespace tc
+
+struct TcParams {
+  const uint8_t* iq;          // [batch][n_cap][2] raw bytes
+  const uint8_t* a_op;        // [3][128][288] UMMA canonical K-major layout
+  const int* soff;            // [n_comb][n_f]
+  const int* smin_all;        // [n_comb] min over all f
+  const float* corr;          // [128][2] (C_re, C_im)
+  float* single_planar;       // [batch][3][n_f][9600]
+  uint32_t n_cap, n_f, n_comb, batch;
+  uint32_t t_tile;            // fold positions per tile
+  uint32_t tiles_per_buf;     // ceil(9600 / t_tile)
+  float inv_scale;            // 1 / (S * 128)
+};
+
+// ---- small PTX wrappers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), no swizzle
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(tc::THREADS, 1) xcorr_fold_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sA = smem + tc::SMEM_A;
+  uint8_t* sP = smem + tc::SMEM_P;
+  float* sPow = reinterpret_cast<float*>(smem + tc::SMEM_POW);
+  const uint32_t bar0 = smem_u32(smem + tc::SMEM_BAR);
+  // barriers: 0,1 p_full[stage]; 2,3 p_empty[stage]; 4,5 tmem_full[buf]; 6,7 tmem_empty[buf]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::SMEM_MISC);
+
+  // ---- one-time setup ----
+  for (int i = tid; i < tc::A_BYTES / 16; i += tc::THREADS)
+    reinterpret_cast<uint4*>(sA)[i] = __ldg(reinterpret_cast<const uint4*>(p.a_op) + i);
+  for (int i = tid; i < 128 * tc::POW_STRIDE; i += tc::THREADS) sPow[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(bar0 + 0, 1); mbar_init(bar0 + 8, 1);      // p_full
+    mbar_init(bar0 + 16, 1); mbar_init(bar0 + 24, 1);    // p_empty (tcgen05.commit)
+    mbar_init(bar0 + 32, 1); mbar_init(bar0 + 40, 1);    // tmem_full (tcgen05.commit)
+    mbar_init(bar0 + 48, 4); mbar_init(bar0 + 56, 4);    // tmem_empty (one arrive per epilogue warp)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(tc::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_async_smem();        // A was written through the generic proxy, the MMA reads it through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t n_items = p.batch * p.tiles_per_buf;
+  const uint32_t n_my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t n_tiles = n_my_items * p.n_comb;
+
+  if (warp == 0) {
+    // ================= P builder =================
+    for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
+      const uint32_t item = blockIdx.x + (tc_i / p.n_comb) * gridDim.x, m = tc_i % p.n_comb;
+      const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
+      const uint32_t stage = tc_i & 1, use = tc_i >> 1;
+      mbar_wait(bar0 + 16 + 8 * stage, (use & 1) ^ 1);   // wait until the MMAs that read this stage retired
+      const int64_t z0 = 2 * ((int64_t)i0 + __ldg(p.smin_all + m));          // byte offset of the tile's first lag
+      const int64_t zlim = 2 * (int64_t)p.n_cap;
+      const uint8_t* zb = p.iq + (size_t)b * p.n_cap * 2;
+      uint4* P1 = reinterpret_cast<uint4*>(sP + (stage * 2 + 0) * tc::P_BYTES);
+      uint4* P2 = reinterpret_cast<uint4*>(sP + (stage * 2 + 1) * tc::P_BYTES);
+      for (int row = lane; row < tc::NBLK * 8; row += 32) {     // row = u*8 + r  -> 16 bytes at z0 + 16u + 2r
+        const int64_t o = z0 + 16 * (row >> 3) + 2 * (row & 7);
+        const int64_t oa = o & ~(int64_t)3;
+        const bool sh = (o & 3) != 0;
+        uint32_t w[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+          const int64_t a = oa + 4 * i;
+          w[i] = (a + 4 <= zlim) ? __ldg(reinterpret_cast<const uint32_t*>(zb + a)) : 0x7f7f7f7fu;
+        }
+        uint32_t x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t v = sh ? __byte_perm(w[i], w[i + 1], 0x5432) : w[i];
+          x[i] = v ^ 0x80808080u;                               // (I', Q') = v - 128
+          y[i] = __byte_perm(v, 0, 0x2301) ^ 0x7F807F80u;       // (Q', ~I')
+        }
+        P1[row] = make_uint4(x[0], x[1], x[2], x[3]);
+        P2[row] = make_uint4(y[0], y[1], y[2], y[3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 0 + 8 * stage);
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole warp walks the pipeline, lane 0 issues) =================
+    const uint32_t sA_addr = smem_u32(sA), sP_addr = smem_u32(sP);
+    uint32_t sc = 0;   // running sub-tile counter -> TMEM buffer
+    for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
+      const uint32_t stage = tc_i & 1, use = tc_i >> 1;
+      mbar_wait(bar0 + 0 + 8 * stage, use & 1);
+      tc_fence_after();
+      for (int q = 0; q < tc::NSUB; q++, sc++) {
+        const uint32_t buf = sc & 1, buse = sc >> 1;
+        mbar_wait(bar0 + 48 + 8 * buf, (buse & 1) ^ 1);      // epilogue drained this accumulator set
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll 1
+          for (int v = 0; v < 2; v++) {
+            const uint32_t pb = sP_addr + (stage * 2 + v) * tc::P_BYTES + q * 4 * 128;
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) {
+              const uint32_t d = tmem_base + buf * 192 + (v * 3 + j) * 32;
+              const uint32_t ab = sA_addr + j * tc::A_TILE_BYTES;
+#pragma unroll
+              for (int s = 0; s < tc::KSTEPS; s++) {
+                const uint64_t da = make_desc(ab + s * 256, 128, tc::KB * 8);   // A: K chunks 128 B apart, row groups 2304 B apart
+                const uint64_t db = make_desc(pb + s * 256, 128, 128);          // Hankel tile: both strides 128 B
+                umma_i8(d, da, db, tc::IDESC, s > 0);
+              }
+            }
+          }
+          umma_commit(bar0 + 32 + 8 * buf);                      // accumulators ready
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(bar0 + 16 + 8 * stage);         // P stage free again
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: TMEM -> |xc|^2 -> fold =================
+    const int quarter = warp & 3;                   // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int L = quarter * 32 + lane;              // template row
+    const uint32_t n_templ = 3 * p.n_f;
+    const bool valid = L < (int)n_templ;
+    const uint32_t f = valid ? L / 3 : 0, t_root = valid ? L % 3 : 0;
+    const float c_re = __ldg(p.corr + 2 * L), c_im = __ldg(p.corr + 2 * L + 1);
+    const float inv = p.inv_scale;
+    float* myPow = sPow + L * tc::POW_STRIDE;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int etid = tid - 64;                      // 0..127
+    uint32_t sc = 0;
+    for (uint32_t it = 0; it < n_my_items; it++) {
+      const uint32_t item = blockIdx.x + it * gridDim.x;
+      const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
+      for (uint32_t m = 0; m < p.n_comb; m++) {
+        const int delta = valid ? __ldg(p.soff + m * p.n_f + f) - __ldg(p.smin_all + m) : 0;
+        for (int q = 0; q < tc::NSUB; q++, sc++) {
+          const uint32_t buf = sc & 1, buse = sc >> 1;
+          mbar_wait(bar0 + 32 + 8 * buf, buse & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 2; h++) {
+            int a[6][16];
+#pragma unroll
+            for (int k = 0; k < 6; k++) tmem_ld16(lane_base + buf * 192 + k * 32 + h * 16, a[k]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+              const float R = fmaf((float)a[0][c], 65536.f, fmaf((float)a[1][c], 256.f, (float)a[2][c])) + c_re;
+              const float I = fmaf((float)a[3][c], 65536.f, fmaf((float)a[4][c], 256.f, (float)a[5][c])) + c_im;
+              const float re = R * inv, im = I * inv;
+              const float pw = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));   // IT++ sqr(complex<float>), searcher.cpp:300
+              const int il = q * 32 + h * 16 + c - delta;
+              if (il >= 0 && il < (int)p.t_tile) myPow[il] = __fadd_rn(myPow[il], pw);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 48 + 8 * buf);
+        }
+      }
+      // ---- item done: write xc_incoherent_single rows (coalesced), reset the accumulators ----
+      epi_bar();
+      const float ncf = (float)p.n_comb;
+      for (uint32_t row = etid >> 5; row < n_templ; row += 4) {
+        const uint32_t rf = row / 3, rt = row % 3;
+        float* dst = p.single_planar + (((size_t)b * 3 + rt) * p.n_f + rf) * LCS_N_FOLD + i0;
+        float* src = sPow + row * tc::POW_STRIDE;
+        for (uint32_t i = lane; i < p.t_tile; i += 32) {
+          if (i0 + i < LCS_N_FOLD) dst[i] = __fdiv_rn(src[i], ncf);   // searcher.cpp:304
+          src[i] = 0.f;
+        }
+      }
+      epi_bar();
+      (void)t_root;
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tc::TMEM_COLS));
+  }
+}
+
+// =============================================================================================
+// Host side
+// =============================================================================================
 lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
   p->tc_ready = false;
+  const XcorrGeom& g = p->geom;
+  if (g.n_f * 3 > 128) return LCS_OK;              // one 128-row M tile of templates (n_f <= 42) for now
+  // fold-offset spread over the whole grid decides how many fold positions a 192-lag tile yields
+  std::vector<int> smin_all(g.n_comb_xc);
+  int spread = 0;
+  for (uint32_t m = 0; m < g.n_comb_xc; m++) {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (uint32_t f = 0; f < g.n_f; f++) {
+      lo = std::min(lo, p->h_soff[(size_t)m * g.n_f + f]);
+      hi = std::max(hi, p->h_soff[(size_t)m * g.n_f + f]);
+    }
+    smin_all[m] = lo;
+    spread = std::max(spread, hi - lo);
+  }
+  if (spread > tc::NT - 64) return LCS_OK;         // grid too sparse for this tiling: FP32 kernel handles it
+  const int t_tile = std::min(tc::T_MAX, tc::NT - spread);
+
+  // scale: power of two with |W*S| <= 127*65536 + 127*256 + 127
+  double maxabs = 0;
+  for (const cd& w : p->h_w) maxabs = std::max(maxabs, std::max(std::fabs(w.real()), std::fabs(w.imag())));
+  const double limit = 127.0 * 65536 + 127 * 256 + 127;
+  int e = (int)std::floor(std::log2(limit / maxabs));
+  while (std::ldexp(maxabs, e) > limit) e--;
+  const double S = std::ldexp(1.0, e);
+
+  std::vector<uint8_t> a_op(tc::A_BYTES, 0);
+  std::vector<float> corr(256, 0.f);
+  auto put = [&](int row, int k, long long wint) {
+    // balanced base-256 digits: wint = 65536 d0 + 256 d1 + d2, d1,d2 in [-128,127]
+    long long d2 = ((wint % 256) + 256) % 256; if (d2 > 127) d2 -= 256;
+    long long r1 = (wint - d2) / 256;
+    long long d1 = ((r1 % 256) + 256) % 256; if (d1 > 127) d1 -= 256;
+    long long d0 = (r1 - d1) / 256;
+    const long long dig[3] = {d0, d1, d2};
+    const int gidx = row >> 3, r = row & 7, c = k >> 4, bb = k & 15;
+    for (int j = 0; j < 3; j++)
+      a_op[(size_t)j * tc::A_TILE_BYTES + (size_t)gidx * (tc::KB * 8) + c * 128 + r * 16 + bb] = (uint8_t)(int8_t)dig[j];
+  };
+  for (uint32_t f = 0; f < g.n_f; f++)
+    for (int t = 0; t < 3; t++) {
+      const int row = (int)f * 3 + t;
+      long long sum_all = 0, sum_even = 0;
+      for (int tap = 0; tap < 137; tap++) {
+        const cd w = p->h_w[((size_t)f * 3 + t) * 137 + tap];
+        const long long wr = std::llrint(w.real() * S), wi = std::llrint(w.imag() * S);
+        put(row, 2 * tap, wr);        // multiplies the I byte
+        put(row, 2 * tap + 1, -wi);   // multiplies the Q byte (re) / ~I byte (im)
+        sum_all += wr - wi;
+        sum_even += wr;
+      }
+      corr[2 * row] = (float)sum_all;      // x = x'+1 :  + sum_j a[j]
+      corr[2 * row + 1] = (float)sum_even; // (Q', ~I') stream:  + sum_m a[2m]
+    }
+  lcs_ctx* ctx = p->ctx;
+  LCS_CUDA(ctx, p->d_tc_a.alloc(a_op.size()));
+  LCS_CUDA(ctx, p->d_tc_meta.alloc(smin_all.size()));
+  LCS_CUDA(ctx, p->d_tc_scale.alloc(corr.size()));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_a.p, a_op.data(), a_op.size(), cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_meta.p, smin_all.data(), smin_all.size() * 4, cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_scale.p, corr.data(), corr.size() * 4, cudaMemcpyHostToDevice));
+  p->tc_params[0] = t_tile;
+  p->tc_params[1] = (LCS_N_FOLD + t_tile - 1) / t_tile;
+  float inv = (float)(1.0 / (S * 128.0));
+  std::memcpy(&p->tc_params[2], &inv, 4);
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+  p->tc_ready = true;
   return LCS_OK;
 }
-int launch_xcorr_fold_tc(lcs_xcorr_plan*, const void*, uint32_t, float*, cudaStream_t) { return 0; }
+
+int launch_xcorr_fold_tc(lcs_xcorr_plan* p, const void* d_iq_cu8, uint32_t batch, float* d_single_planar, cudaStream_t st) {
+  TcParams q;
+  q.iq = reinterpret_cast<const uint8_t*>(d_iq_cu8);
+  q.a_op = p->d_tc_a.p;
+  q.soff = p->d_soff.p;
+  q.smin_all = p->d_tc_meta.p;
+  q.corr = p->d_tc_scale.p;
+  q.single_planar = d_single_planar;
+  q.n_cap = p->geom.n_cap;
+  q.n_f = p->geom.n_f;
+  q.n_comb = p->geom.n_comb_xc;
+  q.batch = batch;
+  q.t_tile = (uint32_t)p->tc_params[0];
+  q.tiles_per_buf = (uint32_t)p->tc_params[1];
+  std::memcpy(&q.inv_scale, &p->tc_params[2], 4);
+  const uint32_t n_items = batch * q.tiles_per_buf;
+  const uint32_t grid = std::min<uint32_t>((uint32_t)p->ctx->n_sm, n_items);
+  xcorr_fold_tc_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(q);
+  return 1;
+}
+
 }  // namespace lcs
