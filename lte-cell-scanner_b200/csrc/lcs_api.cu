@@ -240,6 +240,7 @@ lcs_status lcs_xcorr_plan_create(lcs_ctx* ctx, uint32_t n_cap, const double* f_s
 
 void lcs_xcorr_plan_destroy(lcs_xcorr_plan* plan) {
   if (!plan) return;
+  tc_prof_dump();
   cudaSetDevice(plan->ctx->device);
   cudaDeviceSynchronize();
   for (auto& ev : plan->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }

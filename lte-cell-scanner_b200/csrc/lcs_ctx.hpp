@@ -91,6 +91,7 @@ lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_
 void chain_scratch_release(lcs_ctx* ctx);   // chain_api.cu
 // xcorr_tc.cu
 lcs_status tc_plan_setup(lcs_xcorr_plan* p);
+void tc_prof_dump();
 int launch_xcorr_fold_tc(lcs_xcorr_plan* p, const void* d_iq_cu8, uint32_t batch, float* d_single_planar, cudaStream_t st);
 
 }  // namespace lcs

@@ -173,8 +173,13 @@ int launch_xcorr_fold_fp32(const XcorrGeom& g, const void* d_iq, int iq_format, 
 // One thread = 8 consecutive t of one half frame: a 274-term sum, then 7 slides.  FP64.
 // Output sp_partial[b][m][i] (i<9600); the fold over m happens in the epilogue.
 // ------------------------------------------------------------------------------------------
-constexpr int SP_PER_THREAD = 8;
-constexpr int SP_THREADS = 128;
+// One block = 1024 consecutive t of one half frame: the 1024+273 sample powers are summed with a
+// block-wide FP64 prefix scan, then sp[t] = (S[t+274]-S[t])/274.  For 8-bit IQ every term is a
+// multiple of 2^-14 and every partial sum (< 2^7) is exact in double, so the result is the exactly
+// rounded quotient.
+constexpr int SP_TILE = 1024;
+constexpr int SP_THREADS = 256;
+constexpr int SP_ITEMS = 6;        // 256*6 = 1536 >= 1024+273
 
 template <int FMT>
 __device__ __forceinline__ double pwr(const void* __restrict__ iq, size_t i) {
@@ -189,25 +194,45 @@ __device__ __forceinline__ double pwr(const void* __restrict__ iq, size_t i) {
 template <int FMT>
 __global__ void __launch_bounds__(SP_THREADS) sp_partial_kernel(const void* __restrict__ iq, double* __restrict__ sp_partial,
                                                                 const uint32_t n_cap, const uint32_t n_comb_sp) {
-  const uint32_t m = blockIdx.y, b = blockIdx.z;
-  const uint32_t i_base = (blockIdx.x * SP_THREADS + threadIdx.x) * SP_PER_THREAD;
-  if (i_base >= LCS_N_FOLD) return;
+  __shared__ double ps[SP_THREADS * SP_ITEMS + 1];   // exclusive prefix sums
+  __shared__ double wsum[SP_THREADS / 32];
+  const uint32_t m = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  const uint32_t i_base = blockIdx.x * SP_TILE;
   const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
-  double s = 0;
-  for (int j = 0; j < 274; j++) s += pwr<FMT>(iq, base + j);
-  double* dst = sp_partial + ((size_t)b * n_comb_sp + m) * LCS_N_FOLD + i_base;
-  dst[0] = s / 274;
+  const uint32_t n_need = min((uint32_t)SP_TILE, LCS_N_FOLD - i_base) + 273;   // samples this block touches (all < n_cap)
+  double v[SP_ITEMS], run = 0;
 #pragma unroll
-  for (int q = 1; q < SP_PER_THREAD; q++) {
-    if (i_base + q >= LCS_N_FOLD) break;
-    s += pwr<FMT>(iq, base + 273 + q) - pwr<FMT>(iq, base + q - 1);
-    dst[q] = s / 274;
+  for (int k = 0; k < SP_ITEMS; k++) {
+    const uint32_t e = tid * SP_ITEMS + k;
+    v[k] = e < n_need ? pwr<FMT>(iq, base + e) : 0.0;
+    run += v[k];
   }
+  // block exclusive scan of the per-thread totals
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= (uint32_t)o) incl += t;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  double woff = 0;
+  for (uint32_t w = 0; w < (tid >> 5); w++) woff += wsum[w];
+  double acc = woff + incl - run;
+#pragma unroll
+  for (int k = 0; k < SP_ITEMS; k++) {
+    ps[tid * SP_ITEMS + k] = acc;
+    acc += v[k];
+  }
+  if (tid == SP_THREADS - 1) ps[SP_THREADS * SP_ITEMS] = acc;
+  __syncthreads();
+  double* dst = sp_partial + ((size_t)b * n_comb_sp + m) * LCS_N_FOLD + i_base;
+  for (uint32_t i = tid; i < SP_TILE && i_base + i < LCS_N_FOLD; i += SP_THREADS) dst[i] = (ps[i + 274] - ps[i]) / 274;
 }
 
 int launch_sp_partial(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_partial,
                       cudaStream_t st) {
-  dim3 grid((LCS_N_FOLD + SP_THREADS * SP_PER_THREAD - 1) / (SP_THREADS * SP_PER_THREAD), g.n_comb_sp, batch);
+  dim3 grid((LCS_N_FOLD + SP_TILE - 1) / SP_TILE, g.n_comb_sp, batch);
 #define CALL(F) sp_partial_kernel<F><<<grid, SP_THREADS, 0, st>>>(d_iq, d_sp_partial, g.n_cap, g.n_comb_sp)
   LCS_DISPATCH_FMT(iq_format, CALL);
 #undef CALL
@@ -231,12 +256,14 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__
   const float denom = (float)(2 * arm + 1);
   float best = 0.f;
   int best_f = 0;
+#pragma unroll 4
   for (uint32_t f = 0; f < n_f; f++) {
     const float* sf = s + (size_t)f * LCS_N_FOLD;
-    float v = sf[idx];
+    float v = __ldg(sf + idx);
     for (uint32_t a = 1; a <= arm; a++) {
-      const uint32_t lo = (idx + LCS_N_FOLD - a) % LCS_N_FOLD, hi = (idx + a) % LCS_N_FOLD;
-      v = __fadd_rn(v, __fadd_rn(sf[lo], sf[hi]));  // searcher.cpp:336: += single[idx-t]+single[idx+t]
+      const uint32_t lo = idx >= a ? idx - a : idx + LCS_N_FOLD - a;
+      const uint32_t hi = idx + a < LCS_N_FOLD ? idx + a : idx + a - LCS_N_FOLD;
+      v = __fadd_rn(v, __fadd_rn(__ldg(sf + lo), __ldg(sf + hi)));  // searcher.cpp:336: += single[idx-t]+single[idx+t]
     }
     v = __fdiv_rn(v, denom);  // :343
     if (inc_out) inc_out[(size_t)f * LCS_N_FOLD + idx] = v;
@@ -252,9 +279,79 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__
   }
 }
 
+// Vectorised variant for ds_comb_arm <= 4: one thread = 4 consecutive fold positions, three 128-bit
+// loads per hypothesis (previous / own / next quad; 9600 % 4 == 0 so the circular wrap is a quad index wrap).
+template <int ARM>
+__global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict__ single_planar,
+                                                        const double* __restrict__ sp_partial, double* __restrict__ pow_out,
+                                                        int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
+                                                        float* __restrict__ incoherent_planar, const uint32_t n_f,
+                                                        const uint32_t n_comb_sp) {
+  constexpr uint32_t NQ = LCS_N_FOLD / 4;
+  const uint32_t q = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
+  if (q >= NQ) return;
+  const uint32_t qp = q == 0 ? NQ - 1 : q - 1, qn = q == NQ - 1 ? 0 : q + 1;
+  const float4* s = reinterpret_cast<const float4*>(single_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD);
+  float4* inc_out = incoherent_planar ? reinterpret_cast<float4*>(incoherent_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD) : nullptr;
+  const float denom = (float)(2 * ARM + 1);
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int best_f[4] = {0, 0, 0, 0};
+#pragma unroll 2
+  for (uint32_t f = 0; f < n_f; f++) {
+    const float4* sf = s + (size_t)f * NQ;
+    const float4 c = __ldg(sf + q);
+    float w[12];
+    if (ARM > 0) {
+      const float4 pv = __ldg(sf + qp), nx = __ldg(sf + qn);
+      w[0] = pv.x; w[1] = pv.y; w[2] = pv.z; w[3] = pv.w;
+      w[8] = nx.x; w[9] = nx.y; w[10] = nx.z; w[11] = nx.w;
+    }
+    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
+    float v[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      float x = w[4 + o];
+#pragma unroll
+      for (int a = 1; a <= ARM; a++) x = __fadd_rn(x, __fadd_rn(w[4 + o - a], w[4 + o + a]));  // searcher.cpp:336
+      x = __fdiv_rn(x, denom);                                                             // :343
+      v[o] = x;
+      if (f == 0 || x > best[o]) { best[o] = x; best_f[o] = (int)f; }                      // :371-377
+    }
+    if (inc_out) inc_out[(size_t)f * NQ + q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  const size_t o0 = ((size_t)b * 3 + t) * LCS_N_FOLD + 4 * q;
+  reinterpret_cast<double2*>(pow_out + o0)[0] = make_double2((double)best[0], (double)best[1]);
+  reinterpret_cast<double2*>(pow_out + o0)[1] = make_double2((double)best[2], (double)best[3]);
+  *reinterpret_cast<int4*>(frq_out + o0) = make_int4(best_f[0], best_f[1], best_f[2], best_f[3]);
+  if (t == 0) {
+    const double* sp = sp_partial + (size_t)b * n_comb_sp * LCS_N_FOLD;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      const uint32_t idx = 4 * q + o;
+      double acc = sp[idx];
+      for (uint32_t m = 1; m < n_comb_sp; m++) acc += sp[(size_t)m * LCS_N_FOLD + idx];
+      sp_incoherent[(size_t)b * LCS_N_FOLD + (idx + 137) % LCS_N_FOLD] = acc / n_comb_sp;
+    }
+  }
+}
+
 int launch_epilogue(const XcorrGeom& g, uint32_t batch, const float* d_single_planar, const double* d_sp_partial,
                     double* d_pow, int32_t* d_frq, double* d_sp_incoherent, float* d_incoherent_planar,
                     cudaStream_t st) {
+  if (g.ds_comb_arm <= 4) {
+    dim3 grid((LCS_N_FOLD / 4 + 127) / 128, 3, batch);
+#define EPI(A) epilogue4_kernel<A><<<grid, 128, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent, \
+                                                     d_incoherent_planar, g.n_f, g.n_comb_sp)
+    switch (g.ds_comb_arm) {
+      case 0: EPI(0); break;
+      case 1: EPI(1); break;
+      case 2: EPI(2); break;
+      case 3: EPI(3); break;
+      default: EPI(4); break;
+    }
+#undef EPI
+    return 1;
+  }
   dim3 grid((LCS_N_FOLD + 255) / 256, 3, batch);
   epilogue_kernel<<<grid, 256, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent,
                                         d_incoherent_planar, g.n_f, g.ds_comb_arm, g.n_comb_sp);

@@ -23,6 +23,8 @@
 // 2-5 read the accumulators back (tcgen05.ld), turn them into |xc|^2 and fold the 15 half frames
 // into per-template accumulators in shared memory with each template's own k_factor offset
 // (searcher.cpp:298).  Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 
@@ -31,40 +33,56 @@
 namespace lcs {
 
 namespace tc {
-constexpr int NT = 192;            // lags per tile
-constexpr int NSUB = NT / 32;      // 32-lag MMA sub-tiles per tile
+constexpr int NT = 256;            // lags per tile
+constexpr int NSUBL = 128;         // lags per MMA (UMMA N): one instruction costs max(N,128)/2 cycles (tools/microbench)
+constexpr int NSUB = NT / NSUBL;   // MMA sub-tiles per tile
 constexpr int KB = 288;            // K in bytes: 274 interleaved I/Q taps padded to a multiple of 32
 constexpr int KSTEPS = KB / 32;    // UTCIMMA K = 32 bytes
-constexpr int NBLK = NT / 8 + KB / 16 - 1;   // 41 expanded blocks of 128 B per tile
+constexpr int NBLK = NT / 8 + KB / 16 - 1;   // 49 expanded blocks of 128 B per tile
 constexpr int P_BYTES = NBLK * 128;          // one variant of one stage
+constexpr int A_ROW_WORDS = KB / 4;          // 72 TMEM columns for the digit-0 plane
 constexpr int A_TILE_BYTES = 128 * KB;       // one digit plane: 128 rows x 288 B = 36864
-constexpr int A_BYTES = 3 * A_TILE_BYTES;
-constexpr int T_MAX = 168;         // fold positions per tile (<= NT - max_spread)
-constexpr int POW_STRIDE = T_MAX + 1;
-constexpr int THREADS = 192;
-constexpr int SMEM_A = 0;
-constexpr int SMEM_P = SMEM_A + A_BYTES;                       // [2 stages][2 variants][P_BYTES]
+constexpr int A_BYTES = 3 * A_TILE_BYTES;    // global: [digit0 row-major][digit1 canonical][digit2 canonical]
+constexpr int POW_STRIDE = 223;    // == -1 (mod 32): with fold offsets that decrease along the rows the per-lane
+                                   // read-modify-write addresses of a warp fall into distinct banks
+constexpr int T_MAX = POW_STRIDE - 1;        // fold positions per tile (<= NT - spread)
+// Warp layouts.  COMPACT (3*n_f <= 96, TMEM lanes 96..127 hold padding rows): 16 warps; warp = colgrp*4 + quarter; the
+// quarter-3 warps have no rows to drain, so two of them are the P builder and the MMA issuer -> 128 registers/thread.
+// FULL: 2 service warps + 16 epilogue warps (18 warps -> 96 registers/thread).
+constexpr int THREADS_COMPACT = 512;
+constexpr int THREADS_FULL = 576;
+constexpr int NSLOT = 3;           // accumulator planes in flight
+constexpr int SMEM_A = 0;                                      // digit planes 1 and 2 (UMMA canonical K-major)
+constexpr int SMEM_P = SMEM_A + 2 * A_TILE_BYTES;              // [2 stages][2 variants][P_BYTES]
 constexpr int SMEM_POW = SMEM_P + 4 * P_BYTES;                 // [128][POW_STRIDE] float
-constexpr int SMEM_BAR = SMEM_POW + 128 * POW_STRIDE * 4;      // 8 mbarriers
-constexpr int SMEM_MISC = SMEM_BAR + 8 * 8;
-constexpr int SMEM_TOTAL = SMEM_MISC + 16;
+constexpr int SMEM_BAR = SMEM_POW + 128 * POW_STRIDE * 4;      // 4 + 2*NSLOT mbarriers
+constexpr int SMEM_MISC = SMEM_BAR + 16 * 8;
+constexpr int RAW_CHUNKS = (2 * NT + KB + 16 + 15 + 15) / 16 + 1;   // 16-byte chunks of raw IQ bytes per tile (+ slack)
+constexpr int SMEM_RAW = SMEM_MISC + 16;
+constexpr int SMEM_TOTAL = SMEM_RAW + RAW_CHUNKS * 16 + 16;
+// TMEM map (512 columns): [0,72) the most significant int8 digit plane of the templates (A operand of the
+// .ts MMA form); [128,512) a ring of three accumulator planes of 128 lags x int32 (one (digit, re/im) product each).
 constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_ACC0 = 128;
+constexpr uint32_t TMEM_SLOT = 128;
 // UTCIMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) bits[4,6);
 // a_format / b_format = 1 (signed 8 bit) bits [7,10) / [10,13); K-major A and B; N>>3 bits [17,23); M>>4 bits [24,29)
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NSUBL >> 3) << 17) | ((128u >> 4) << 24);
 }  // namespace tc
 
 struct TcParams {
   const uint8_t* iq;          // [batch][n_cap][2] raw bytes
-  const uint8_t* a_op;        // [3][128][288] UMMA canonical K-major layout
+  const uint8_t* a_op;        // digit 0 [128][288] row-major, then digits 1,2 in UMMA canonical K-major order
   const int* soff;            // [n_comb][n_f]
-  const int* smin_all;        // [n_comb] min over all f
+  const int* smin_all;        // [n_comb] min over the chunk's f
   const float* corr;          // [128][2] (C_re, C_im)
   float* single_planar;       // [batch][3][n_f][9600]
-  uint32_t n_cap, n_f, n_comb, batch;
+  uint32_t n_cap, n_f, n_comb, batch;   // n_f = hypotheses in this chunk (<= 42)
+  uint32_t f0, n_f_total;     // first hypothesis of the chunk / size of the whole grid
   uint32_t t_tile;            // fold positions per tile
   uint32_t tiles_per_buf;     // ceil(9600 / t_tile)
   float inv_scale;            // 1 / (S * 128)
+  long long* prof;            // optional [grid][8] cycle counters (NULL = off)
 };
 
 // ---- small PTX wrappers ----
@@ -101,6 +119,51 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t d
       "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (M rows on the 128 lanes, K bytes packed along the columns), B from shared memory.
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// Variants guarded by an "elected lane" flag so that the issuing warp stays convergent: the compiler then keeps
+// descriptors in uniform registers and emits one UTCIMMA per call instead of an elect-and-loop sequence.
+__device__ __forceinline__ uint32_t elect_one_flag() {
+  uint32_t r;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void umma_i8_ts_g(uint32_t flag, uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate), "r"(flag)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_g(uint32_t flag, uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(flag)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_g(uint32_t flag, uint32_t bar) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar), "r"(flag) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -111,70 +174,114 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-__global__ void __launch_bounds__(tc::THREADS, 1) xcorr_fold_tc_kernel(const TcParams p) {
+template <bool COMPACT>
+__device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
+  constexpr int NTHREADS = COMPACT ? tc::THREADS_COMPACT : tc::THREADS_FULL;
+  constexpr int N_EPI_WARPS = COMPACT ? 12 : 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // roles
+  const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31 are accessible to this warp
+  const int ewarp = COMPACT ? warp : warp - 2;                     // epilogue numbering
+  const int colgrp = ewarp >> 2;                                  // which 32 of the 128 sub-tile columns
+  const bool is_pbuilder = COMPACT ? (warp == 3) : (warp == 0);
+  const bool is_mma = COMPACT ? (warp == 7) : (warp == 1);
+  const bool is_epi = COMPACT ? (quarter != 3) : (warp >= 2);
   uint8_t* sA = smem + tc::SMEM_A;
   uint8_t* sP = smem + tc::SMEM_P;
   float* sPow = reinterpret_cast<float*>(smem + tc::SMEM_POW);
   const uint32_t bar0 = smem_u32(smem + tc::SMEM_BAR);
-  // barriers: 0,1 p_full[stage]; 2,3 p_empty[stage]; 4,5 tmem_full[buf]; 6,7 tmem_empty[buf]
+  // barriers (8 B each): 0,1 p_full[stage]; 2,3 p_empty[stage]; 4.. acc_full[slot]; 4+NSLOT.. acc_empty[slot]
+  const uint32_t BAR_PFULL = bar0, BAR_PEMPTY = bar0 + 16, BAR_AFULL = bar0 + 32, BAR_AEMPTY = bar0 + 32 + 8 * tc::NSLOT;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::SMEM_MISC);
 
   // ---- one-time setup ----
-  for (int i = tid; i < tc::A_BYTES / 16; i += tc::THREADS)
-    reinterpret_cast<uint4*>(sA)[i] = __ldg(reinterpret_cast<const uint4*>(p.a_op) + i);
-  for (int i = tid; i < 128 * tc::POW_STRIDE; i += tc::THREADS) sPow[i] = 0.f;
+  for (int i = tid; i < 2 * tc::A_TILE_BYTES / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(sA)[i] = __ldg(reinterpret_cast<const uint4*>(p.a_op + tc::A_TILE_BYTES) + i);
+  for (int i = tid; i < 128 * tc::POW_STRIDE; i += NTHREADS) sPow[i] = 0.f;
   if (tid == 0) {
-    mbar_init(bar0 + 0, 1); mbar_init(bar0 + 8, 1);      // p_full
-    mbar_init(bar0 + 16, 1); mbar_init(bar0 + 24, 1);    // p_empty (tcgen05.commit)
-    mbar_init(bar0 + 32, 1); mbar_init(bar0 + 40, 1);    // tmem_full (tcgen05.commit)
-    mbar_init(bar0 + 48, 4); mbar_init(bar0 + 56, 4);    // tmem_empty (one arrive per epilogue warp)
+    mbar_init(BAR_PFULL, 1); mbar_init(BAR_PFULL + 8, 1);
+    mbar_init(BAR_PEMPTY, 1); mbar_init(BAR_PEMPTY + 8, 1);            // tcgen05.commit
+    for (int i = 0; i < tc::NSLOT; i++) { mbar_init(BAR_AFULL + 8 * i, 1); mbar_init(BAR_AEMPTY + 8 * i, N_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+  if (is_mma) {  // TMEM allocation (whole warp), address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"(tc::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  fence_async_smem();        // A was written through the generic proxy, the MMA reads it through the async proxy
+  fence_async_smem();        // digit planes 1,2 were written through the generic proxy, the MMA reads them through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 4 && warp < 8) {
+    // Digit-0 plane -> TMEM: lane = template row, 72 columns (288 int8).
+    const int row = quarter * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint4* src = reinterpret_cast<const uint4*>(p.a_op + (size_t)row * tc::KB);
+    for (int c = 0; c < tc::A_ROW_WORDS / 8; c++) {
+      const uint4 lo = __ldg(src + 2 * c), hi = __ldg(src + 2 * c + 1);
+      const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      tmem_st8(tl + c * 8, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const uint32_t n_items = p.batch * p.tiles_per_buf;
   const uint32_t n_my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t n_tiles = n_my_items * p.n_comb;
 
-  if (warp == 0) {
+  if (is_pbuilder) {
     // ================= P builder =================
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
       const uint32_t item = blockIdx.x + (tc_i / p.n_comb) * gridDim.x, m = tc_i % p.n_comb;
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
       const uint32_t stage = tc_i & 1, use = tc_i >> 1;
-      mbar_wait(bar0 + 16 + 8 * stage, (use & 1) ^ 1);   // wait until the MMAs that read this stage retired
+      mbar_wait(BAR_PEMPTY + 8 * stage, (use & 1) ^ 1);   // wait until the MMAs that read this stage retired
       const int64_t z0 = 2 * ((int64_t)i0 + __ldg(p.smin_all + m));          // byte offset of the tile's first lag
-      const int64_t zlim = 2 * (int64_t)p.n_cap;
       const uint8_t* zb = p.iq + (size_t)b * p.n_cap * 2;
+      // Stage the tile's raw bytes (2*NT + KB + alignment slack < 1 KB) with coalesced 128-bit loads, then expand
+      // from shared memory: the expansion reads every byte 16 times, global memory only once.
+      const int64_t zal = z0 & ~(int64_t)15;
+      const int64_t zend = (int64_t)(p.batch - b) * p.n_cap * 2;              // bytes left in the whole allocation
+      uint4* raw = reinterpret_cast<uint4*>(smem + tc::SMEM_RAW);
+      for (int c = lane; c < tc::RAW_CHUNKS; c += 32) {
+        const int64_t a = zal + 16 * c;
+        raw[c] = (a + 16 <= zend) ? __ldg(reinterpret_cast<const uint4*>(zb + a)) : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+      }
+      __syncwarp();
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw);
+      const int zo = (int)(z0 - zal);
       uint4* P1 = reinterpret_cast<uint4*>(sP + (stage * 2 + 0) * tc::P_BYTES);
       uint4* P2 = reinterpret_cast<uint4*>(sP + (stage * 2 + 1) * tc::P_BYTES);
+#pragma unroll 2
       for (int row = lane; row < tc::NBLK * 8; row += 32) {     // row = u*8 + r  -> 16 bytes at z0 + 16u + 2r
-        const int64_t o = z0 + 16 * (row >> 3) + 2 * (row & 7);
-        const int64_t oa = o & ~(int64_t)3;
+        const int o = zo + 16 * (row >> 3) + 2 * (row & 7);
+        const int ow = o >> 2;
         const bool sh = (o & 3) != 0;
         uint32_t w[5];
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-          const int64_t a = oa + 4 * i;
-          w[i] = (a + 4 <= zlim) ? __ldg(reinterpret_cast<const uint32_t*>(zb + a)) : 0x7f7f7f7fu;
-        }
+        for (int i = 0; i < 5; i++) w[i] = rw[ow + i];
         uint32_t x[4], y[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -185,112 +292,185 @@ __global__ void __launch_bounds__(tc::THREADS, 1) xcorr_fold_tc_kernel(const TcP
         P1[row] = make_uint4(x[0], x[1], x[2], x[3]);
         P2[row] = make_uint4(y[0], y[1], y[2], y[3]);
       }
-      fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 0 + 8 * stage);
+      fence_async_smem();      // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_PFULL + 8 * stage);
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer (whole warp walks the pipeline, lane 0 issues) =================
-    const uint32_t sA_addr = smem_u32(sA), sP_addr = smem_u32(sP);
-    uint32_t sc = 0;   // running sub-tile counter -> TMEM buffer
+  } else if (is_mma) {
+    // ================= MMA issuer: the whole warp walks the pipeline convergently, one elected lane issues ====
+    const uint32_t sP_addr = smem_u32(sP), sA_addr = smem_u32(sA);
+    const uint32_t flag = elect_one_flag();
+    // descriptors advance by adding to the 14-bit (address >> 4) field: +16 per 256-byte K step
+    const uint64_t a_desc1 = make_desc(sA_addr, 128, tc::KB * 8), a_desc2 = make_desc(sA_addr + tc::A_TILE_BYTES, 128, tc::KB * 8);
+    uint32_t jb = 0;   // running job counter: one job = one (sub-tile, re/im, digit) product into one accumulator plane
+    long long t_pwait = 0, t_ewait = 0, t_start = clock64();
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
       const uint32_t stage = tc_i & 1, use = tc_i >> 1;
-      mbar_wait(bar0 + 0 + 8 * stage, use & 1);
+      long long c0 = clock64();
+      mbar_wait(BAR_PFULL + 8 * stage, use & 1);
+      t_pwait += clock64() - c0;
       tc_fence_after();
-      for (int q = 0; q < tc::NSUB; q++, sc++) {
-        const uint32_t buf = sc & 1, buse = sc >> 1;
-        mbar_wait(bar0 + 48 + 8 * buf, (buse & 1) ^ 1);      // epilogue drained this accumulator set
-        tc_fence_after();
-        if (lane == 0) {
 #pragma unroll 1
-          for (int v = 0; v < 2; v++) {
-            const uint32_t pb = sP_addr + (stage * 2 + v) * tc::P_BYTES + q * 4 * 128;
+      for (int q = 0; q < tc::NSUB; q++) {
 #pragma unroll 1
-            for (int j = 0; j < 3; j++) {
-              const uint32_t d = tmem_base + buf * 192 + (v * 3 + j) * 32;
-              const uint32_t ab = sA_addr + j * tc::A_TILE_BYTES;
+        for (int v = 0; v < 2; v++) {
+          const uint64_t b_desc = make_desc(sP_addr + (stage * 2 + v) * tc::P_BYTES + q * (tc::NSUBL / 8) * 128, 128, 128);
 #pragma unroll
-              for (int s = 0; s < tc::KSTEPS; s++) {
-                const uint64_t da = make_desc(ab + s * 256, 128, tc::KB * 8);   // A: K chunks 128 B apart, row groups 2304 B apart
-                const uint64_t db = make_desc(pb + s * 256, 128, 128);          // Hankel tile: both strides 128 B
-                umma_i8(d, da, db, tc::IDESC, s > 0);
-              }
+          for (int j = 0; j < 3; j++, jb++) {
+            const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
+            c0 = clock64();
+            mbar_wait(BAR_AEMPTY + 8 * slot, (suse & 1) ^ 1);      // epilogue drained this accumulator plane
+            t_ewait += clock64() - c0;
+            tc_fence_after();
+            const uint32_t d = tmem_base + tc::TMEM_ACC0 + slot * tc::TMEM_SLOT;
+            if (j == 0) {
+#pragma unroll
+              for (int s = 0; s < tc::KSTEPS; s++) umma_i8_ts_g(flag, d, tmem_base + s * 8, b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
+            } else {
+              const uint64_t a_desc = j == 1 ? a_desc1 : a_desc2;
+#pragma unroll
+              for (int s = 0; s < tc::KSTEPS; s++)
+                umma_i8_g(flag, d, a_desc + (uint64_t)(s * 16), b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
             }
+            umma_commit_g(flag, BAR_AFULL + 8 * slot);              // plane ready
           }
-          umma_commit(bar0 + 32 + 8 * buf);                      // accumulators ready
         }
-        __syncwarp();
       }
-      if (lane == 0) umma_commit(bar0 + 16 + 8 * stage);         // P stage free again
-      __syncwarp();
+      umma_commit_g(flag, BAR_PEMPTY + 8 * stage);                  // P stage free again
     }
-  } else {
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = clock64() - t_start;
+      p.prof[blockIdx.x * 8 + 1] = t_pwait;
+      p.prof[blockIdx.x * 8 + 2] = t_ewait;
+      p.prof[blockIdx.x * 8 + 3] = jb;
+    }
+  } else if (is_epi) {
     // ================= epilogue: TMEM -> |xc|^2 -> fold =================
-    const int quarter = warp & 3;                   // TMEM lanes 32*quarter .. +31 belong to this warp
     const int L = quarter * 32 + lane;              // template row
     const uint32_t n_templ = 3 * p.n_f;
     const bool valid = L < (int)n_templ;
-    const uint32_t f = valid ? L / 3 : 0, t_root = valid ? L % 3 : 0;
-    const float c_re = __ldg(p.corr + 2 * L), c_im = __ldg(p.corr + 2 * L + 1);
-    const float inv = p.inv_scale;
+    const uint32_t f = valid ? L / 3 : 0;
+    const float2 c_re2 = make_float2(__ldg(p.corr + 2 * L), __ldg(p.corr + 2 * L));
+    const float2 c_im2 = make_float2(__ldg(p.corr + 2 * L + 1), __ldg(p.corr + 2 * L + 1));
+    const float inv2s = p.inv_scale * p.inv_scale;  // inv_scale is a power of two: scaling commutes with the roundings
+    const float2 inv2 = make_float2(inv2s, inv2s), w256 = make_float2(256.f, 256.f);
     float* myPow = sPow + L * tc::POW_STRIDE;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int etid = tid - 64;                      // 0..127
-    uint32_t sc = 0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + tc::TMEM_ACC0 + colgrp * 32;
+    const bool warp_has_rows = COMPACT || (uint32_t)(quarter * 32) < n_templ;   // FULL layout: trailing quarters may be padding
+    uint32_t jb = 0;
+    long long t_fwait = 0, t_ld = 0, e_start = clock64();
     for (uint32_t it = 0; it < n_my_items; it++) {
       const uint32_t item = blockIdx.x + it * gridDim.x;
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
       for (uint32_t m = 0; m < p.n_comb; m++) {
-        const int delta = valid ? __ldg(p.soff + m * p.n_f + f) - __ldg(p.smin_all + m) : 0;
-        for (int q = 0; q < tc::NSUB; q++, sc++) {
-          const uint32_t buf = sc & 1, buse = sc >> 1;
-          mbar_wait(bar0 + 32 + 8 * buf, buse & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int h = 0; h < 2; h++) {
-            int a[6][16];
+        const int delta = valid ? __ldg(p.soff + m * p.n_f_total + p.f0 + f) - __ldg(p.smin_all + m) : 0;
+        for (int q = 0; q < tc::NSUB; q++) {
+          if (!warp_has_rows) {            // padding rows: only keep the accumulator ring moving
+            for (int k = 0; k < 6; k++, jb++) {
+              const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
+              mbar_wait(BAR_AFULL + 8 * slot, suse & 1);
+              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);
+              __syncwarp();
+            }
+            continue;
+          }
+          // Recombine the three digit planes: t = a0*256 + a1 (int32, exact), value = float(t)*256 + float(a2).
+          // Planes arrive in the order (re: d0,d1,d2, im: d0,d1,d2); d0 and d1 are fetched together.
+          float2 RR[16];        // squared real parts, two columns per register pair
+          const int il0 = q * tc::NSUBL + colgrp * 32 - delta;
+          const bool inside = __all_sync(0xffffffffu, il0 >= 0 && il0 + 32 <= (int)p.t_tile);
 #pragma unroll
-            for (int k = 0; k < 6; k++) tmem_ld16(lane_base + buf * 192 + k * 32 + h * 16, a[k]);
-            tmem_ld_wait();
+          for (int v = 0; v < 2; v++) {
+            int t[32], a[32];
+            {
+              const uint32_t s0 = jb % tc::NSLOT, u0 = jb / tc::NSLOT, s1 = (jb + 1) % tc::NSLOT, u1 = (jb + 1) / tc::NSLOT;
+              long long c0 = clock64();
+              mbar_wait(BAR_AFULL + 8 * s0, u0 & 1);
+              mbar_wait(BAR_AFULL + 8 * s1, u1 & 1);
+              long long c1 = clock64();
+              t_fwait += c1 - c0;
+              tc_fence_after();
+              tmem_ld16(lane_base + s0 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&t[0]));
+              tmem_ld16(lane_base + s0 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&t[16]));
+              tmem_ld16(lane_base + s1 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&a[0]));
+              tmem_ld16(lane_base + s1 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
+              tmem_ld_wait();
+              t_ld += clock64() - c1;
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) { mbar_arrive(BAR_AEMPTY + 8 * s0); mbar_arrive(BAR_AEMPTY + 8 * s1); }   // both planes are in registers
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-              const float R = fmaf((float)a[0][c], 65536.f, fmaf((float)a[1][c], 256.f, (float)a[2][c])) + c_re;
-              const float I = fmaf((float)a[3][c], 65536.f, fmaf((float)a[4][c], 256.f, (float)a[5][c])) + c_im;
-              const float re = R * inv, im = I * inv;
-              const float pw = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));   // IT++ sqr(complex<float>), searcher.cpp:300
-              const int il = q * 32 + h * 16 + c - delta;
-              if (il >= 0 && il < (int)p.t_tile) myPow[il] = __fadd_rn(myPow[il], pw);
+              for (int c = 0; c < 32; c++) t[c] = t[c] * 256 + a[c];
+              jb += 2;
+            }
+            {
+              const uint32_t s2 = jb % tc::NSLOT, u2 = jb / tc::NSLOT;
+              long long c0 = clock64();
+              mbar_wait(BAR_AFULL + 8 * s2, u2 & 1);
+              long long c1 = clock64();
+              t_fwait += c1 - c0;
+              tc_fence_after();
+              tmem_ld16(lane_base + s2 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&a[0]));
+              tmem_ld16(lane_base + s2 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
+              tmem_ld_wait();
+              t_ld += clock64() - c1;
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * s2);
+              jb += 1;
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float2 hi = make_float2((float)t[c], (float)t[c + 1]);
+              const float2 lo = make_float2((float)a[c], (float)a[c + 1]);
+              float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), v == 0 ? c_re2 : c_im2);
+              x = __fmul2_rn(x, x);
+              if (v == 0) {
+                RR[c >> 1] = x;
+              } else {
+                // IT++ sqr(complex<float>) (searcher.cpp:300): re*re+im*im un-fused; the power-of-two scale commutes
+                const float2 pw = __fmul2_rn(__fadd2_rn(RR[c >> 1], x), inv2);
+                const int il = il0 + c;
+                if (inside || (unsigned)il < p.t_tile) myPow[il] = __fadd_rn(myPow[il], pw.x);
+                if (inside || (unsigned)(il + 1) < p.t_tile) myPow[il + 1] = __fadd_rn(myPow[il + 1], pw.y);
+              }
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar0 + 48 + 8 * buf);
         }
       }
       // ---- item done: write xc_incoherent_single rows (coalesced), reset the accumulators ----
-      epi_bar();
+      epi_bar(32 * N_EPI_WARPS);
       const float ncf = (float)p.n_comb;
-      for (uint32_t row = etid >> 5; row < n_templ; row += 4) {
+      const uint32_t erank = COMPACT ? (uint32_t)(colgrp * 3 + quarter) : (uint32_t)ewarp;   // dense 0..N_EPI_WARPS-1
+      for (uint32_t row = erank; row < n_templ; row += N_EPI_WARPS) {
         const uint32_t rf = row / 3, rt = row % 3;
-        float* dst = p.single_planar + (((size_t)b * 3 + rt) * p.n_f + rf) * LCS_N_FOLD + i0;
+        float* dst = p.single_planar + (((size_t)b * 3 + rt) * p.n_f_total + p.f0 + rf) * LCS_N_FOLD + i0;
         float* src = sPow + row * tc::POW_STRIDE;
         for (uint32_t i = lane; i < p.t_tile; i += 32) {
           if (i0 + i < LCS_N_FOLD) dst[i] = __fdiv_rn(src[i], ncf);   // searcher.cpp:304
           src[i] = 0.f;
         }
       }
-      epi_bar();
-      (void)t_root;
+      epi_bar(32 * N_EPI_WARPS);
+    }
+    if (p.prof && lane == 0 && colgrp == 0 && quarter == 0) {
+      p.prof[blockIdx.x * 8 + 4] = clock64() - e_start;
+      p.prof[blockIdx.x * 8 + 5] = t_fwait;
+      p.prof[blockIdx.x * 8 + 6] = t_ld;
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (is_mma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tc::TMEM_COLS));
   }
 }
+
+__global__ void __maxnreg__(128) xcorr_fold_tc_kernel_compact(const TcParams p) { xcorr_fold_tc_body<true>(p); }
+__global__ void __maxnreg__(96) xcorr_fold_tc_kernel_full(const TcParams p) { xcorr_fold_tc_body<false>(p); }
 
 // =============================================================================================
 // Host side
@@ -298,20 +478,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1) xcorr_fold_tc_kernel(const TcP
 lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
   p->tc_ready = false;
   const XcorrGeom& g = p->geom;
-  if (g.n_f * 3 > 128) return LCS_OK;              // one 128-row M tile of templates (n_f <= 42) for now
-  // fold-offset spread over the whole grid decides how many fold positions a 192-lag tile yields
-  std::vector<int> smin_all(g.n_comb_xc);
+  // Hypotheses are processed in chunks of <= 42 (3*42 = 126 template rows of the 128-row M tile).
+  const uint32_t n_chunks = (g.n_f + 41) / 42;
+  const uint32_t chunk = (g.n_f + n_chunks - 1) / n_chunks;
+  if (n_chunks > 8) return LCS_OK;
+  // fold-offset spread inside a chunk decides how many fold positions a 256-lag tile yields
+  std::vector<int> smin((size_t)n_chunks * g.n_comb_xc);
   int spread = 0;
-  for (uint32_t m = 0; m < g.n_comb_xc; m++) {
-    int lo = INT32_MAX, hi = INT32_MIN;
-    for (uint32_t f = 0; f < g.n_f; f++) {
-      lo = std::min(lo, p->h_soff[(size_t)m * g.n_f + f]);
-      hi = std::max(hi, p->h_soff[(size_t)m * g.n_f + f]);
+  for (uint32_t c = 0; c < n_chunks; c++)
+    for (uint32_t m = 0; m < g.n_comb_xc; m++) {
+      int lo = INT32_MAX, hi = INT32_MIN;
+      for (uint32_t f = c * chunk; f < std::min(g.n_f, (c + 1) * chunk); f++) {
+        lo = std::min(lo, p->h_soff[(size_t)m * g.n_f + f]);
+        hi = std::max(hi, p->h_soff[(size_t)m * g.n_f + f]);
+      }
+      smin[(size_t)c * g.n_comb_xc + m] = lo;
+      spread = std::max(spread, hi - lo);
     }
-    smin_all[m] = lo;
-    spread = std::max(spread, hi - lo);
-  }
-  if (spread > tc::NT - 64) return LCS_OK;         // grid too sparse for this tiling: FP32 kernel handles it
+  if (spread > tc::NT - 64) return LCS_OK;         // grid too sparse for this tiling: the FP32 kernel handles it
   const int t_tile = std::min(tc::T_MAX, tc::NT - spread);
 
   // scale: power of two with |W*S| <= 127*65536 + 127*256 + 127
@@ -322,22 +506,25 @@ lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
   while (std::ldexp(maxabs, e) > limit) e--;
   const double S = std::ldexp(1.0, e);
 
-  std::vector<uint8_t> a_op(tc::A_BYTES, 0);
-  std::vector<float> corr(256, 0.f);
-  auto put = [&](int row, int k, long long wint) {
-    // balanced base-256 digits: wint = 65536 d0 + 256 d1 + d2, d1,d2 in [-128,127]
-    long long d2 = ((wint % 256) + 256) % 256; if (d2 > 127) d2 -= 256;
-    long long r1 = (wint - d2) / 256;
-    long long d1 = ((r1 % 256) + 256) % 256; if (d1 > 127) d1 -= 256;
-    long long d0 = (r1 - d1) / 256;
-    const long long dig[3] = {d0, d1, d2};
-    const int gidx = row >> 3, r = row & 7, c = k >> 4, bb = k & 15;
-    for (int j = 0; j < 3; j++)
-      a_op[(size_t)j * tc::A_TILE_BYTES + (size_t)gidx * (tc::KB * 8) + c * 128 + r * 16 + bb] = (uint8_t)(int8_t)dig[j];
-  };
-  for (uint32_t f = 0; f < g.n_f; f++)
+  std::vector<uint8_t> a_op((size_t)n_chunks * tc::A_BYTES, 0);
+  std::vector<float> corr((size_t)n_chunks * 256, 0.f);
+  for (uint32_t f = 0; f < g.n_f; f++) {
+    const uint32_t c = f / chunk, fl = f - c * chunk;
+    uint8_t* ac = a_op.data() + (size_t)c * tc::A_BYTES;
+    auto put = [&](int row, int k, long long wint) {
+      // balanced base-256 digits: wint = 65536 d0 + 256 d1 + d2, d1,d2 in [-128,127]
+      long long d2 = ((wint % 256) + 256) % 256; if (d2 > 127) d2 -= 256;
+      long long r1 = (wint - d2) / 256;
+      long long d1 = ((r1 % 256) + 256) % 256; if (d1 > 127) d1 -= 256;
+      long long d0 = (r1 - d1) / 256;
+      const long long dig[3] = {d0, d1, d2};
+      ac[(size_t)row * tc::KB + k] = (uint8_t)(int8_t)dig[0];                    // digit 0: row-major (goes to TMEM)
+      const int gidx = row >> 3, r = row & 7, c = k >> 4, bb = k & 15;           // digits 1,2: UMMA canonical K-major
+      for (int j = 1; j < 3; j++)
+        ac[(size_t)j * tc::A_TILE_BYTES + (size_t)gidx * (tc::KB * 8) + c * 128 + r * 16 + bb] = (uint8_t)(int8_t)dig[j];
+    };
     for (int t = 0; t < 3; t++) {
-      const int row = (int)f * 3 + t;
+      const int row = (int)fl * 3 + t;
       long long sum_all = 0, sum_even = 0;
       for (int tap = 0; tap < 137; tap++) {
         const cd w = p->h_w[((size_t)f * 3 + t) * 137 + tap];
@@ -347,44 +534,74 @@ lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
         sum_all += wr - wi;
         sum_even += wr;
       }
-      corr[2 * row] = (float)sum_all;      // x = x'+1 :  + sum_j a[j]
-      corr[2 * row + 1] = (float)sum_even; // (Q', ~I') stream:  + sum_m a[2m]
+      corr[(size_t)c * 256 + 2 * row] = (float)sum_all;       // x = x'+1 :  + sum_j a[j]
+      corr[(size_t)c * 256 + 2 * row + 1] = (float)sum_even;  // (Q', ~I') stream:  + sum_m a[2m]
     }
+  }
   lcs_ctx* ctx = p->ctx;
   LCS_CUDA(ctx, p->d_tc_a.alloc(a_op.size()));
-  LCS_CUDA(ctx, p->d_tc_meta.alloc(smin_all.size()));
+  LCS_CUDA(ctx, p->d_tc_meta.alloc(smin.size()));
   LCS_CUDA(ctx, p->d_tc_scale.alloc(corr.size()));
   LCS_CUDA(ctx, cudaMemcpy(p->d_tc_a.p, a_op.data(), a_op.size(), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_meta.p, smin_all.data(), smin_all.size() * 4, cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_meta.p, smin.data(), smin.size() * 4, cudaMemcpyHostToDevice));
   LCS_CUDA(ctx, cudaMemcpy(p->d_tc_scale.p, corr.data(), corr.size() * 4, cudaMemcpyHostToDevice));
   p->tc_params[0] = t_tile;
   p->tc_params[1] = (LCS_N_FOLD + t_tile - 1) / t_tile;
   float inv = (float)(1.0 / (S * 128.0));
   std::memcpy(&p->tc_params[2], &inv, 4);
-  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+  p->tc_params[3] = (int)n_chunks;
+  p->tc_params[4] = (int)chunk;
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel_full, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
   p->tc_ready = true;
   return LCS_OK;
 }
 
+// LCS_TC_PROF=1 : per-CTA cycle counters of the pipeline stages are collected and printed at exit (debug aid).
+static long long* g_prof = nullptr;
+static long long* tc_prof_buffer() {
+  static int on = -1;
+  if (on < 0) on = std::getenv("LCS_TC_PROF") ? 1 : 0;
+  if (!on) return nullptr;
+  if (!g_prof) { cudaMalloc((void**)&g_prof, 148 * 8 * 8); cudaMemset(g_prof, 0, 148 * 8 * 8); }
+  return g_prof;
+}
+void tc_prof_dump() {
+  if (!g_prof) return;
+  std::vector<long long> h(148 * 8);
+  cudaDeviceSynchronize();
+  cudaMemcpy(h.data(), g_prof, h.size() * 8, cudaMemcpyDeviceToHost);
+  for (int b : {0, 1, 73, 147})
+    std::printf("[tc prof] cta %3d: mma total %lld  wait_P %lld  wait_acc_empty %lld  jobs %lld | epi total %lld  wait_acc_full %lld  tmem_ld %lld\n", b, h[b * 8], h[b * 8 + 1],
+                h[b * 8 + 2], h[b * 8 + 3], h[b * 8 + 4], h[b * 8 + 5], h[b * 8 + 6]);
+}
+
 int launch_xcorr_fold_tc(lcs_xcorr_plan* p, const void* d_iq_cu8, uint32_t batch, float* d_single_planar, cudaStream_t st) {
-  TcParams q;
-  q.iq = reinterpret_cast<const uint8_t*>(d_iq_cu8);
-  q.a_op = p->d_tc_a.p;
-  q.soff = p->d_soff.p;
-  q.smin_all = p->d_tc_meta.p;
-  q.corr = p->d_tc_scale.p;
-  q.single_planar = d_single_planar;
-  q.n_cap = p->geom.n_cap;
-  q.n_f = p->geom.n_f;
-  q.n_comb = p->geom.n_comb_xc;
-  q.batch = batch;
-  q.t_tile = (uint32_t)p->tc_params[0];
-  q.tiles_per_buf = (uint32_t)p->tc_params[1];
-  std::memcpy(&q.inv_scale, &p->tc_params[2], 4);
-  const uint32_t n_items = batch * q.tiles_per_buf;
-  const uint32_t grid = std::min<uint32_t>((uint32_t)p->ctx->n_sm, n_items);
-  xcorr_fold_tc_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(q);
-  return 1;
+  const uint32_t n_chunks = (uint32_t)p->tc_params[3], chunk = (uint32_t)p->tc_params[4];
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    TcParams q;
+    q.iq = reinterpret_cast<const uint8_t*>(d_iq_cu8);
+    q.a_op = p->d_tc_a.p + (size_t)c * tc::A_BYTES;
+    q.soff = p->d_soff.p;
+    q.smin_all = p->d_tc_meta.p + (size_t)c * p->geom.n_comb_xc;
+    q.corr = p->d_tc_scale.p + (size_t)c * 256;
+    q.single_planar = d_single_planar;
+    q.n_cap = p->geom.n_cap;
+    q.f0 = c * chunk;
+    q.n_f = std::min(chunk, p->geom.n_f - q.f0);
+    q.n_f_total = p->geom.n_f;
+    q.n_comb = p->geom.n_comb_xc;
+    q.batch = batch;
+    q.t_tile = (uint32_t)p->tc_params[0];
+    q.tiles_per_buf = (uint32_t)p->tc_params[1];
+    std::memcpy(&q.inv_scale, &p->tc_params[2], 4);
+    q.prof = tc_prof_buffer();
+    const uint32_t n_items = batch * q.tiles_per_buf;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)p->ctx->n_sm, n_items);
+    if (3 * q.n_f <= 96) xcorr_fold_tc_kernel_compact<<<grid, tc::THREADS_COMPACT, tc::SMEM_TOTAL, st>>>(q);
+    else xcorr_fold_tc_kernel_full<<<grid, tc::THREADS_FULL, tc::SMEM_TOTAL, st>>>(q);
+  }
+  return (int)n_chunks;
 }
 
 }  // namespace lcs

@@ -226,3 +226,80 @@ def test_cellsearch_cli_full_test(tmp_path, capbuf0000):
     out2 = subprocess.run([os.path.join(host, "CellSearch_b200"), "-s", "739000000", "-l", "--raw", "-b", "-d", str(tmp_path)],
                           capture_output=True, text=True, timeout=300)
     assert out2.returncode == 0 and len([l for l in out2.stdout.splitlines() if re.match(r"^\s*27[17]\s+2\s", l)]) == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# Tensor-core correlator (tcgen05 kind::i8, exact integer arithmetic for 8-bit IQ)
+# ---------------------------------------------------------------------------------------------
+def _tc_vs_oracle(ctx, lcs, oracle, cu8_batch, f, fcr, fcp, fs, arm=2):
+    plan = ctx.plan(cu8_batch.shape[1], f, arm, fcr, fcp, fs, max_batch=cu8_batch.shape[0], kernel=lcs.KERNEL_TC)
+    assert plan.kernel_for(lcs.IQ_CU8) == lcs.KERNEL_TC
+    out = plan.run_host_np(cu8_batch, lcs.IQ_CU8)
+    for b in range(cu8_batch.shape[0]):
+        ref = oracle.xcorr_pss(cu8_to_c128(cu8_batch[b]), f, arm, fcr, fcp, fs)
+        assert rel_err(out["single"][b].transpose(0, 2, 1), ref["single"]) < 5e-7      # exact integers + 2 float roundings
+        assert rel_err(out["pow"][b], ref["pow"]) < 5e-7
+        assert np.abs(out["sp_incoherent"][b] / ref["sp_incoherent"] - 1).max() < 1e-12
+        assert frq_mismatch_is_near_tie(out["frq"][b], ref)
+    plan.close()
+    return out
+
+
+def test_tc_capbuf_0000(ctx, lcs, oracle, capbuf0000):
+    f = oracle.f_search_set(capbuf0000["fc"], 120.0)
+    _tc_vs_oracle(ctx, lcs, oracle, capbuf0000["cu8"][None], f, 739e6, 739e6, 1.92e6)
+
+
+def test_tc_synthetic_batch_and_extremes(ctx, lcs, oracle):
+    """Batch of 3 incl. a full-scale buffer (bytes 0 and 255 everywhere: the int8 edge cases of the
+    v-128 / ~I representation) and an all-127 (zero signal) buffer."""
+    rng = np.random.default_rng(11)
+    full = rng.choice(np.array([0, 255], np.uint8), size=(153600, 2))
+    zero = np.full((153600, 2), 127, np.uint8)
+    cu8 = np.stack([synth_cu8(0xC0FFEE), full, zero])
+    f = oracle.f_search_set(739e6, 20.0)
+    plan = ctx.plan(153600, f, 2, 739e6, 739e6, 1.92e6, max_batch=3, kernel=lcs.KERNEL_TC)
+    out = plan.run_host_np(cu8, lcs.IQ_CU8)
+    for b in range(2):
+        ref = oracle.xcorr_pss(cu8_to_c128(cu8[b]), f, 2, 739e6, 739e6, 1.92e6)
+        assert rel_err(out["single"][b].transpose(0, 2, 1), ref["single"]) < 5e-7
+        assert frq_mismatch_is_near_tie(out["frq"][b], ref)
+    assert np.all(out["single"][2] == 0) and np.all(out["pow"][2] == 0) and np.all(out["sp_incoherent"][2] == 0)
+    plan.close()
+
+
+def test_tc_edge_shapes(ctx, lcs, oracle):
+    """n_f=1, n_f=42 (one full 126-row chunk), 51 (two chunks), short buffer, fc_programmed != fc_requested, arm=0/1."""
+    cases = [
+        (153600, np.array([35000.0]), 2, 739e6, 739e6, 1.92e6),
+        (40000, np.arange(-20, 22) * 2500.0, 2, 739e6, 739.002e6, 1.92e6 * 1.00001),
+        (29000, np.array([-20000.0, 0.0, 5000.0]), 0, 2.1e9, 2.1e9, 1.92e6),
+        (30000, np.arange(-25, 26) * 3000.0, 1, 739e6, 739e6, 1.92e6),          # 51 hypotheses -> 2 chunks
+    ]
+    for i, (n_cap, f, arm, fcr, fcp, fs) in enumerate(cases):
+        _tc_vs_oracle(ctx, lcs, oracle, synth_cu8(77 + i, n_cap)[None], f, fcr, fcp, fs, arm)
+
+
+def test_tc_matches_fp32_kernel_and_auto_selection(ctx, lcs):
+    """Same plan parameters, both kernels: powers agree to fp32 noise; AUTO picks TC for cu8 only."""
+    f = lcs.f_search_set(739e6, 100.0)
+    cu8 = np.stack([synth_cu8(5), synth_cu8(6)])
+    res = {}
+    for k in (lcs.KERNEL_TC, lcs.KERNEL_FP32, lcs.KERNEL_AUTO):
+        plan = ctx.plan(153600, f, 2, 739e6, 739e6, 1.92e6, max_batch=2, kernel=k)
+        if k == lcs.KERNEL_AUTO:
+            assert plan.kernel_for(lcs.IQ_CU8) == lcs.KERNEL_TC and plan.kernel_for(lcs.IQ_CF32) == lcs.KERNEL_FP32
+        res[k] = plan.run_host_np(cu8, lcs.IQ_CU8)
+        plan.close()
+    a, b = res[lcs.KERNEL_TC]["single"], res[lcs.KERNEL_FP32]["single"]
+    assert np.abs(a - b).max() < 1e-6 * b.max()
+    assert np.array_equal(res[lcs.KERNEL_AUTO]["single"], a)
+    # wide grids (3*n_f > 128 template rows) run as several <=42-hypothesis chunks
+    wide = np.arange(-30, 31) * 2000.0
+    outs = {}
+    for k in (lcs.KERNEL_TC, lcs.KERNEL_FP32):
+        plan = ctx.plan(153600, wide, 2, 739e6, 739e6, 1.92e6, max_batch=1, kernel=k)
+        outs[k] = plan.run_host_np(cu8[:1], lcs.IQ_CU8)
+        plan.close()
+    assert np.abs(outs[lcs.KERNEL_TC]["single"] - outs[lcs.KERNEL_FP32]["single"]).max() < 1e-6 * outs[lcs.KERNEL_FP32]["single"].max()
+    assert (outs[lcs.KERNEL_TC]["frq"] != outs[lcs.KERNEL_FP32]["frq"]).mean() < 0.002

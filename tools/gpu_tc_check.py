@@ -46,7 +46,7 @@ for name, c, f, batch in cases:
 # timing, bench shape
 import torch
 f = O.f_search_set(739e6, 100.0)
-B = 16
+B = 24
 plan = ctx.plan(153600, f, 2, 739e6, 739e6, 1.92e6, max_batch=B, kernel=L.KERNEL_TC)
 iq = torch.from_numpy(np.stack([synth(100 + i) for i in range(B)])).cuda()
 single = torch.empty((B, 3, f.size, 9600), dtype=torch.float32, device="cuda")

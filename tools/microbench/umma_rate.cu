@@ -1,0 +1,79 @@
+// Microbenchmark: cycles per tcgen05.mma instruction vs N, kind (i8 / f16-bf16) and A source (smem / tmem).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu ; run on a B200.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+template <int KIND, int ATMEM>
+__device__ __forceinline__ void mma(uint32_t d, uint32_t at, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (KIND == 0) {
+    if (ATMEM) asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(at), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    else asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+  } else {
+    if (ATMEM) asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;}" ::"r"(d), "r"(at), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    else asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+  }
+}
+template <int KIND, int ATMEM>
+__global__ void bench(int N, int iters, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * 1024; i += blockDim.x) smem[i] = (uint8_t)(i * 7);
+  if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tslot;
+  if (tid == 0) {
+    // i8: c S32(2), a,b signed(1); f16: c F32(1), a,b BF16(1)
+    uint32_t idesc = KIND == 0 ? ((2u << 4) | (1u << 7) | (1u << 10)) : ((1u << 4) | (1u << 7) | (1u << 10));
+    idesc |= ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32 * 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+      const uint64_t da = make_desc(sa + (i & 7) * 256, 128, 2304), db = make_desc(sb + (i & 7) * 256, 128, 128);
+      mma<KIND, ATMEM>(tb + 256, tb + (i & 7) * 8, da, db, idesc, i > 0);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("{.reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0; @p bra D; bra W; D: }" ::"r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+}
+template <int KIND, int ATMEM>
+void run(const char* name) {
+  long long* d;
+  cudaMalloc(&d, 8);
+  cudaFuncSetAttribute(bench<KIND, ATMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int N : {16, 32, 64, 96, 128, 192, 256}) {
+    if (N > 256) continue;
+    const int iters = 2000;
+    bench<KIND, ATMEM><<<1, 128, 64 * 1024>>>(N, iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    printf("%-22s M=128 N=%3d K=32B : %7.1f cycles/MMA  (%s)\n", name, N, (double)c / iters, cudaGetErrorString(e));
+  }
+  cudaFree(d);
+}
+int main() {
+  run<0, 0>("i8  A=smem");
+  run<0, 1>("i8  A=tmem");
+  run<1, 0>("bf16 A=smem");
+  run<1, 1>("bf16 A=tmem");
+  return 0;
+}
