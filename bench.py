@@ -67,42 +67,66 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms 20` process runs across the region; only samples stamped inside it are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
-        self.stop_flag = threading.Event()
+        self.proc = None
+        self.t0 = self.t1 = None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)          # let the first samples arrive before the region starts
+        except Exception:
+            self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=3)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            import datetime
+            for line in out.splitlines():
+                r = [x.strip() for x in line.split(",")]
+                if len(r) < 9:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    ts = None
+                rows.append((ts, r))
+        inside = [r for ts, r in rows if ts is not None and self.t0 is not None and self.t0 - 0.02 <= ts <= self.t1 + 0.02]
+        use = inside if inside else [r for _, r in rows]
+        sm = [float(r[1]) for r in use if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in use if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in use if r[3].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+        for r in use:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(self.rows))
+                    power_w_max=max(pw) if pw else None, reasons=sorted(reasons), samples=len(inside),
+                    samples_total=len(rows))
 
 
 def host_threads():
@@ -190,9 +214,9 @@ def cpu_baseline_leg(f, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="capture buffers per rank per step")
+    ap.add_argument("--batch", type=int, default=192, help="capture buffers per rank per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,7 +250,7 @@ def main():
 
     # ---- synthetic inputs: a ring of distinct batches whose inputs+outputs exceed L2 (126 MB) ----
     out_bytes_per_cap = 3 * n_f * 9600 * 4 + 3 * 9600 * 12 + 9600 * 8
-    ring = max(2, int(np.ceil(300e6 / (B * (out_bytes_per_cap + N_CAP * 2)))))
+    ring = max(2, int(np.ceil(300e6 / (B * (out_bytes_per_cap + N_CAP * 2)))))      # inputs+outputs in flight > L2 (126 MB)
     base = np.stack([synth_cu8(SEED0 + rank * 100003 + i) for i in range(B)])      # [B][n_cap][2] u8
     h_iq = torch.from_numpy(base).pin_memory()
     d_iq, d_single, d_pow, d_frq, d_spi = [], [], [], [], []
@@ -262,12 +286,14 @@ def main():
     launches0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for i in range(args.steps):
             step(args.warmup + i)
         e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     kernel_ms, kernel_n = plan.timing_read()
     plan.timing_enable(False)
@@ -312,7 +338,10 @@ def main():
         alg_bytes = B * b_alg(n_f, in_bps)
         alg_flops = B * f_alg(n_f)
         if kernel_used == "xcorr_fold_tc":
-            roof = {"bound": "tensor", "achieved": alg_flops / k_avg_s / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+            roof = {"bound": "tensor", "achieved": alg_flops / k_avg_s / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "tensor_mode": "tcgen05 kind::i8 (s8 x s8 -> s32, exact); the driver measures only a bf16 peak, int8 runs at 2x "
+                                   "that rate; achieved counts F_alg only - the kernel executes 3 int8 digit planes x 128/93 row padding "
+                                   "x 288/274 K padding x 256/228 tile overlap = 4.9x more MACs than F_alg"}
         else:
             roof = {"bound": "hbm", "achieved": alg_bytes / k_avg_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
@@ -325,7 +354,7 @@ def main():
         line = {
             "metric": "IQ Msamp/s through xcorr_pss", "value": value, "unit": "Msamp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kernel_used == "xcorr_fold_fp32" else "bf16x3-exact",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kernel_used == "xcorr_fold_fp32" else "s8 (3 exact int8 digits, int32 accumulate)",
             "data": "synthetic",
             "config": {"workload": "xcorr_pss 153600-sample capbuf, n_f=31 (+-100 ppm @739 MHz), 3 PSS roots, ds_comb_arm=2",
                        "capbufs_per_step_per_gpu": B, "capbufs_per_s": capbufs_per_s, "n_f": n_f, "iq_format": "cu8",

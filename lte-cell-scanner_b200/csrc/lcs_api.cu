@@ -118,8 +118,9 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
 static int resolve_kernel(const lcs_xcorr_plan* p, int iq_format) {
   if (p->kernel == LCS_KERNEL_FP32) return LCS_KERNEL_FP32;
   if (p->kernel == LCS_KERNEL_TC) return LCS_KERNEL_TC;
-  // AUTO: the tensor-core kernel is exact only for 8-bit IQ
-  return (iq_format == LCS_IQ_CU8 && p->tc_ready) ? LCS_KERNEL_TC : LCS_KERNEL_FP32;
+  // AUTO: the tensor-core kernel is exact only for 8-bit IQ; its cost is flat in n_f (one 128-row M tile per <=42
+  // hypotheses) while the FP32 kernel's is proportional to n_f, so tiny grids (tracker mode, n_f=1) stay on FP32.
+  return (iq_format == LCS_IQ_CU8 && p->tc_ready && p->geom.n_f >= 4) ? LCS_KERNEL_TC : LCS_KERNEL_FP32;
 }
 
 static lcs_status run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single,

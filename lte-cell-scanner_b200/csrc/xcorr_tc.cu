@@ -40,10 +40,10 @@ constexpr int KB = 288;            // K in bytes: 274 interleaved I/Q taps padde
 constexpr int KSTEPS = KB / 32;    // UTCIMMA K = 32 bytes
 constexpr int NBLK = NT / 8 + KB / 16 - 1;   // 49 expanded blocks of 128 B per tile
 constexpr int P_BYTES = NBLK * 128;          // one variant of one stage
-constexpr int A_ROW_WORDS = KB / 4;          // 72 TMEM columns for the digit-0 plane
+constexpr int A_ROW_WORDS = KB / 4;          // 72 TMEM columns per digit plane
 constexpr int A_TILE_BYTES = 128 * KB;       // one digit plane: 128 rows x 288 B = 36864
-constexpr int A_BYTES = 3 * A_TILE_BYTES;    // global: [digit0 row-major][digit1 canonical][digit2 canonical]
-constexpr int POW_STRIDE = 223;    // == -1 (mod 32): with fold offsets that decrease along the rows the per-lane
+constexpr int A_BYTES = 3 * A_TILE_BYTES;    // global: [3 digits][128 rows][288 B], row-major
+constexpr int POW_STRIDE = 255;    // == -1 (mod 32): with fold offsets that decrease along the rows the per-lane
                                    // read-modify-write addresses of a warp fall into distinct banks
 constexpr int T_MAX = POW_STRIDE - 1;        // fold positions per tile (<= NT - spread)
 // Warp layouts.  COMPACT (3*n_f <= 96, TMEM lanes 96..127 hold padding rows): 16 warps; warp = colgrp*4 + quarter; the
@@ -51,19 +51,19 @@ constexpr int T_MAX = POW_STRIDE - 1;        // fold positions per tile (<= NT -
 // FULL: 2 service warps + 16 epilogue warps (18 warps -> 96 registers/thread).
 constexpr int THREADS_COMPACT = 512;
 constexpr int THREADS_FULL = 576;
-constexpr int NSLOT = 3;           // accumulator planes in flight
-constexpr int SMEM_A = 0;                                      // digit planes 1 and 2 (UMMA canonical K-major)
-constexpr int SMEM_P = SMEM_A + 2 * A_TILE_BYTES;              // [2 stages][2 variants][P_BYTES]
+constexpr int NSLOT = 2;           // accumulator planes in flight
+constexpr int SMEM_P = 0;                                      // [2 stages][2 variants][P_BYTES]
 constexpr int SMEM_POW = SMEM_P + 4 * P_BYTES;                 // [128][POW_STRIDE] float
 constexpr int SMEM_BAR = SMEM_POW + 128 * POW_STRIDE * 4;      // 4 + 2*NSLOT mbarriers
 constexpr int SMEM_MISC = SMEM_BAR + 16 * 8;
 constexpr int RAW_CHUNKS = (2 * NT + KB + 16 + 15 + 15) / 16 + 1;   // 16-byte chunks of raw IQ bytes per tile (+ slack)
 constexpr int SMEM_RAW = SMEM_MISC + 16;
 constexpr int SMEM_TOTAL = SMEM_RAW + RAW_CHUNKS * 16 + 16;
-// TMEM map (512 columns): [0,72) the most significant int8 digit plane of the templates (A operand of the
-// .ts MMA form); [128,512) a ring of three accumulator planes of 128 lags x int32 (one (digit, re/im) product each).
+// TMEM map (512 columns): [0,216) the three int8 digit planes of the templates (A operand of the .ts MMA form: the
+// tensor core then reads only the Hankel tile from shared memory, half the operand traffic of the .ss form);
+// [256,512) two accumulator planes of 128 lags x int32 (one (digit, re/im) product each), used alternately.
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_ACC0 = 128;
+constexpr uint32_t TMEM_ACC0 = 256;
 constexpr uint32_t TMEM_SLOT = 128;
 // UTCIMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) bits[4,6);
 // a_format / b_format = 1 (signed 8 bit) bits [7,10) / [10,13); K-major A and B; N>>3 bits [17,23); M>>4 bits [24,29)
@@ -72,7 +72,7 @@ constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NSUB
 
 struct TcParams {
   const uint8_t* iq;          // [batch][n_cap][2] raw bytes
-  const uint8_t* a_op;        // digit 0 [128][288] row-major, then digits 1,2 in UMMA canonical K-major order
+  const uint8_t* a_op;        // [3 digits][128 rows][288] int8, row-major
   const int* soff;            // [n_comb][n_f]
   const int* smin_all;        // [n_comb] min over the chunk's f
   const float* corr;          // [128][2] (C_re, C_im)
@@ -203,7 +203,6 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
   const bool is_pbuilder = COMPACT ? (warp == 3) : (warp == 0);
   const bool is_mma = COMPACT ? (warp == 7) : (warp == 1);
   const bool is_epi = COMPACT ? (quarter != 3) : (warp >= 2);
-  uint8_t* sA = smem + tc::SMEM_A;
   uint8_t* sP = smem + tc::SMEM_P;
   float* sPow = reinterpret_cast<float*>(smem + tc::SMEM_POW);
   const uint32_t bar0 = smem_u32(smem + tc::SMEM_BAR);
@@ -212,8 +211,6 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::SMEM_MISC);
 
   // ---- one-time setup ----
-  for (int i = tid; i < 2 * tc::A_TILE_BYTES / 16; i += NTHREADS)
-    reinterpret_cast<uint4*>(sA)[i] = __ldg(reinterpret_cast<const uint4*>(p.a_op + tc::A_TILE_BYTES) + i);
   for (int i = tid; i < 128 * tc::POW_STRIDE; i += NTHREADS) sPow[i] = 0.f;
   if (tid == 0) {
     mbar_init(BAR_PFULL, 1); mbar_init(BAR_PFULL + 8, 1);
@@ -226,20 +223,21 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
                  "r"(tc::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  fence_async_smem();        // digit planes 1,2 were written through the generic proxy, the MMA reads them through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp >= 4 && warp < 8) {
-    // Digit-0 plane -> TMEM: lane = template row, 72 columns (288 int8).
+    // Template digit planes -> TMEM: lane = template row, 72 columns (288 int8) per digit.
     const int row = quarter * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint4* src = reinterpret_cast<const uint4*>(p.a_op + (size_t)row * tc::KB);
-    for (int c = 0; c < tc::A_ROW_WORDS / 8; c++) {
-      const uint4 lo = __ldg(src + 2 * c), hi = __ldg(src + 2 * c + 1);
-      const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-      tmem_st8(tl + c * 8, v);
+    for (int j = 0; j < 3; j++) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.a_op + ((size_t)j * 128 + row) * tc::KB);
+      for (int c = 0; c < tc::A_ROW_WORDS / 8; c++) {
+        const uint4 lo = __ldg(src + 2 * c), hi = __ldg(src + 2 * c + 1);
+        const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tmem_st8(tl + j * tc::A_ROW_WORDS + c * 8, v);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -299,10 +297,9 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
     }
   } else if (is_mma) {
     // ================= MMA issuer: the whole warp walks the pipeline convergently, one elected lane issues ====
-    const uint32_t sP_addr = smem_u32(sP), sA_addr = smem_u32(sA);
+    const uint32_t sP_addr = smem_u32(sP);
     const uint32_t flag = elect_one_flag();
     // descriptors advance by adding to the 14-bit (address >> 4) field: +16 per 256-byte K step
-    const uint64_t a_desc1 = make_desc(sA_addr, 128, tc::KB * 8), a_desc2 = make_desc(sA_addr + tc::A_TILE_BYTES, 128, tc::KB * 8);
     uint32_t jb = 0;   // running job counter: one job = one (sub-tile, re/im, digit) product into one accumulator plane
     long long t_pwait = 0, t_ewait = 0, t_start = clock64();
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
@@ -324,15 +321,9 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
             t_ewait += clock64() - c0;
             tc_fence_after();
             const uint32_t d = tmem_base + tc::TMEM_ACC0 + slot * tc::TMEM_SLOT;
-            if (j == 0) {
 #pragma unroll
-              for (int s = 0; s < tc::KSTEPS; s++) umma_i8_ts_g(flag, d, tmem_base + s * 8, b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
-            } else {
-              const uint64_t a_desc = j == 1 ? a_desc1 : a_desc2;
-#pragma unroll
-              for (int s = 0; s < tc::KSTEPS; s++)
-                umma_i8_g(flag, d, a_desc + (uint64_t)(s * 16), b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
-            }
+            for (int s = 0; s < tc::KSTEPS; s++)
+              umma_i8_ts_g(flag, d, tmem_base + j * tc::A_ROW_WORDS + s * 8, b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
             umma_commit_g(flag, BAR_AFULL + 8 * slot);              // plane ready
           }
         }
@@ -376,64 +367,74 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
             continue;
           }
           // Recombine the three digit planes: t = a0*256 + a1 (int32, exact), value = float(t)*256 + float(a2).
-          // Planes arrive in the order (re: d0,d1,d2, im: d0,d1,d2); d0 and d1 are fetched together.
+          // Planes arrive in the order (re: d0,d1,d2, im: d0,d1,d2); each is released as soon as it is in registers.
           float2 RR[16];        // squared real parts, two columns per register pair
           const int il0 = q * tc::NSUBL + colgrp * 32 - delta;
           const bool inside = __all_sync(0xffffffffu, il0 >= 0 && il0 + 32 <= (int)p.t_tile);
 #pragma unroll
           for (int v = 0; v < 2; v++) {
             int t[32], a[32];
-            {
-              const uint32_t s0 = jb % tc::NSLOT, u0 = jb / tc::NSLOT, s1 = (jb + 1) % tc::NSLOT, u1 = (jb + 1) / tc::NSLOT;
-              long long c0 = clock64();
-              mbar_wait(BAR_AFULL + 8 * s0, u0 & 1);
-              mbar_wait(BAR_AFULL + 8 * s1, u1 & 1);
-              long long c1 = clock64();
+#pragma unroll
+            for (int j = 0; j < 3; j++, jb++) {
+              const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
+              long long c0 = p.prof ? clock64() : 0;
+              mbar_wait(BAR_AFULL + 8 * slot, suse & 1);
+              long long c1 = p.prof ? clock64() : 0;
               t_fwait += c1 - c0;
               tc_fence_after();
-              tmem_ld16(lane_base + s0 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&t[0]));
-              tmem_ld16(lane_base + s0 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&t[16]));
-              tmem_ld16(lane_base + s1 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&a[0]));
-              tmem_ld16(lane_base + s1 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
-              tmem_ld_wait();
-              t_ld += clock64() - c1;
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) { mbar_arrive(BAR_AEMPTY + 8 * s0); mbar_arrive(BAR_AEMPTY + 8 * s1); }   // both planes are in registers
-#pragma unroll
-              for (int c = 0; c < 32; c++) t[c] = t[c] * 256 + a[c];
-              jb += 2;
-            }
-            {
-              const uint32_t s2 = jb % tc::NSLOT, u2 = jb / tc::NSLOT;
-              long long c0 = clock64();
-              mbar_wait(BAR_AFULL + 8 * s2, u2 & 1);
-              long long c1 = clock64();
-              t_fwait += c1 - c0;
-              tc_fence_after();
-              tmem_ld16(lane_base + s2 * tc::TMEM_SLOT, *reinterpret_cast<int(*)[16]>(&a[0]));
-              tmem_ld16(lane_base + s2 * tc::TMEM_SLOT + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
-              tmem_ld_wait();
-              t_ld += clock64() - c1;
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * s2);
-              jb += 1;
-            }
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float2 hi = make_float2((float)t[c], (float)t[c + 1]);
-              const float2 lo = make_float2((float)a[c], (float)a[c + 1]);
-              float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), v == 0 ? c_re2 : c_im2);
-              x = __fmul2_rn(x, x);
-              if (v == 0) {
-                RR[c >> 1] = x;
+              const uint32_t src = lane_base + slot * tc::TMEM_SLOT;
+              if (j == 0) {
+                tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&t[0]));
+                tmem_ld16(src + 16, *reinterpret_cast<int(*)[16]>(&t[16]));
               } else {
-                // IT++ sqr(complex<float>) (searcher.cpp:300): re*re+im*im un-fused; the power-of-two scale commutes
-                const float2 pw = __fmul2_rn(__fadd2_rn(RR[c >> 1], x), inv2);
-                const int il = il0 + c;
-                if (inside || (unsigned)il < p.t_tile) myPow[il] = __fadd_rn(myPow[il], pw.x);
-                if (inside || (unsigned)(il + 1) < p.t_tile) myPow[il + 1] = __fadd_rn(myPow[il + 1], pw.y);
+                tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&a[0]));
+                tmem_ld16(src + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
+              }
+              tmem_ld_wait();
+              if (p.prof) t_ld += clock64() - c1;
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);   // plane is in registers
+              if (j == 1) {
+#pragma unroll
+                for (int c = 0; c < 32; c++) t[c] = t[c] * 256 + a[c];
+              }
+            }
+            if (v == 0) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 2) {
+                const float2 hi = make_float2((float)t[c], (float)t[c + 1]);
+                const float2 lo = make_float2((float)a[c], (float)a[c + 1]);
+                const float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), c_re2);
+                RR[c >> 1] = __fmul2_rn(x, x);
+              }
+            } else {
+              // IT++ sqr(complex<float>) (searcher.cpp:300): re*re+im*im un-fused; the power-of-two scale commutes.
+              // Fold in batches of 8 columns: 8 loads in flight, then 8 adds, then 8 stores.
+#pragma unroll
+              for (int c0 = 0; c0 < 32; c0 += 8) {
+                float pwv[8], cur[8];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                  const float2 hi = make_float2((float)t[c0 + c], (float)t[c0 + c + 1]);
+                  const float2 lo = make_float2((float)a[c0 + c], (float)a[c0 + c + 1]);
+                  float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), c_im2);
+                  x = __fmul2_rn(x, x);
+                  const float2 pw = __fmul2_rn(__fadd2_rn(RR[(c0 + c) >> 1], x), inv2);
+                  pwv[c] = pw.x;
+                  pwv[c + 1] = pw.y;
+                }
+                float* dstp = myPow + il0 + c0;
+                if (inside) {
+#pragma unroll
+                  for (int c = 0; c < 8; c++) cur[c] = dstp[c];
+#pragma unroll
+                  for (int c = 0; c < 8; c++) dstp[c] = __fadd_rn(cur[c], pwv[c]);
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 8; c++)
+                    if ((unsigned)(il0 + c0 + c) < p.t_tile) dstp[c] = __fadd_rn(dstp[c], pwv[c]);
+                }
               }
             }
           }
@@ -518,10 +519,7 @@ lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
       long long d1 = ((r1 % 256) + 256) % 256; if (d1 > 127) d1 -= 256;
       long long d0 = (r1 - d1) / 256;
       const long long dig[3] = {d0, d1, d2};
-      ac[(size_t)row * tc::KB + k] = (uint8_t)(int8_t)dig[0];                    // digit 0: row-major (goes to TMEM)
-      const int gidx = row >> 3, r = row & 7, c = k >> 4, bb = k & 15;           // digits 1,2: UMMA canonical K-major
-      for (int j = 1; j < 3; j++)
-        ac[(size_t)j * tc::A_TILE_BYTES + (size_t)gidx * (tc::KB * 8) + c * 128 + r * 16 + bb] = (uint8_t)(int8_t)dig[j];
+      for (int j = 0; j < 3; j++) ac[((size_t)j * 128 + row) * tc::KB + k] = (uint8_t)(int8_t)dig[j];   // row-major, goes to TMEM
     };
     for (int t = 0; t < 3; t++) {
       const int row = (int)fl * 3 + t;
