@@ -30,6 +30,17 @@
 
 #include "lcs_ctx.hpp"
 
+// Build with -DLCS_TC_PROFILE=1 to collect per-CTA cycle counters of the pipeline stages (printed when a plan is
+// destroyed with LCS_TC_PROF=1 in the environment); off by default so that the clock reads cost nothing.
+#ifndef LCS_TC_PROFILE
+#define LCS_TC_PROFILE 0
+#endif
+#if LCS_TC_PROFILE
+#define TC_CLK() clock64()
+#else
+#define TC_CLK() 0ll
+#endif
+
 namespace lcs {
 
 namespace tc {
@@ -301,12 +312,12 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
     const uint32_t flag = elect_one_flag();
     // descriptors advance by adding to the 14-bit (address >> 4) field: +16 per 256-byte K step
     uint32_t jb = 0;   // running job counter: one job = one (sub-tile, re/im, digit) product into one accumulator plane
-    long long t_pwait = 0, t_ewait = 0, t_start = clock64();
+    long long t_pwait = 0, t_ewait = 0, t_start = TC_CLK();
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
       const uint32_t stage = tc_i & 1, use = tc_i >> 1;
-      long long c0 = clock64();
+      long long c0 = TC_CLK();
       mbar_wait(BAR_PFULL + 8 * stage, use & 1);
-      t_pwait += clock64() - c0;
+      t_pwait += TC_CLK() - c0;
       tc_fence_after();
 #pragma unroll 1
       for (int q = 0; q < tc::NSUB; q++) {
@@ -316,9 +327,9 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
 #pragma unroll
           for (int j = 0; j < 3; j++, jb++) {
             const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
-            c0 = clock64();
+            c0 = TC_CLK();
             mbar_wait(BAR_AEMPTY + 8 * slot, (suse & 1) ^ 1);      // epilogue drained this accumulator plane
-            t_ewait += clock64() - c0;
+            t_ewait += TC_CLK() - c0;
             tc_fence_after();
             const uint32_t d = tmem_base + tc::TMEM_ACC0 + slot * tc::TMEM_SLOT;
 #pragma unroll
@@ -330,8 +341,8 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       }
       umma_commit_g(flag, BAR_PEMPTY + 8 * stage);                  // P stage free again
     }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 8 + 0] = clock64() - t_start;
+    if (LCS_TC_PROFILE && p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = TC_CLK() - t_start;
       p.prof[blockIdx.x * 8 + 1] = t_pwait;
       p.prof[blockIdx.x * 8 + 2] = t_ewait;
       p.prof[blockIdx.x * 8 + 3] = jb;
@@ -350,7 +361,7 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + tc::TMEM_ACC0 + colgrp * 32;
     const bool warp_has_rows = COMPACT || (uint32_t)(quarter * 32) < n_templ;   // FULL layout: trailing quarters may be padding
     uint32_t jb = 0;
-    long long t_fwait = 0, t_ld = 0, e_start = clock64();
+    long long t_fwait = 0, t_ld = 0, e_start = TC_CLK();
     for (uint32_t it = 0; it < n_my_items; it++) {
       const uint32_t item = blockIdx.x + it * gridDim.x;
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
@@ -377,9 +388,9 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
 #pragma unroll
             for (int j = 0; j < 3; j++, jb++) {
               const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
-              long long c0 = p.prof ? clock64() : 0;
+              long long c0 = TC_CLK();
               mbar_wait(BAR_AFULL + 8 * slot, suse & 1);
-              long long c1 = p.prof ? clock64() : 0;
+              long long c1 = TC_CLK();
               t_fwait += c1 - c0;
               tc_fence_after();
               const uint32_t src = lane_base + slot * tc::TMEM_SLOT;
@@ -391,7 +402,7 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
                 tmem_ld16(src + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
               }
               tmem_ld_wait();
-              if (p.prof) t_ld += clock64() - c1;
+              t_ld += TC_CLK() - c1;
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);   // plane is in registers
@@ -455,8 +466,8 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       }
       epi_bar(32 * N_EPI_WARPS);
     }
-    if (p.prof && lane == 0 && colgrp == 0 && quarter == 0) {
-      p.prof[blockIdx.x * 8 + 4] = clock64() - e_start;
+    if (LCS_TC_PROFILE && p.prof && lane == 0 && colgrp == 0 && quarter == 0) {
+      p.prof[blockIdx.x * 8 + 4] = TC_CLK() - e_start;
       p.prof[blockIdx.x * 8 + 5] = t_fwait;
       p.prof[blockIdx.x * 8 + 6] = t_ld;
     }
