@@ -63,6 +63,7 @@ struct lcs_xcorr_plan {
   lcs::DevBuf<unsigned char> d_tc_a;   // packed template operand
   lcs::DevBuf<int> d_tc_meta;
   lcs::DevBuf<float> d_tc_scale;
+  lcs::DevBuf<int16_t> d_tc_dsh;       // per-chunk fold-offset tables
   int tc_params[16] = {0};
   // kernel timing hook
   bool timing = false;

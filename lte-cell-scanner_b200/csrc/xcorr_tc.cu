@@ -1,28 +1,35 @@
 // xcorr_tc.cu - PSS correlator on the 5th-generation tensor cores (tcgen05 / TMEM), exact for 8-bit IQ.
 //
-// The sliding correlation is a Toeplitz GEMM: D[template, lag] = sum_j A[template, j] * z[2*lag + j],
+// The sliding correlation is a Toeplitz GEMM: D[lag, template] = sum_j z[2*lag + j] * W[template, j],
 // j = 0..273 over the interleaved I/Q byte stream z of the capture buffer (rtl-sdr wire format,
 // reference src/capbuf.cpp:157-181).  Everything is done in EXACT integer arithmetic:
 //
 //   * IQ bytes v are used as signed x' = v-128 (a XOR with 0x80; the true sample is (x'+1)/128),
 //   * each template component W (double, conj(fshift(pss_td))/137 of searcher.cpp:145-151) is scaled by
 //     a power of two S and rounded to a 24-bit integer, split into three balanced base-256 digits
-//     W*S = 65536 a0 + 256 a1 + a2, a_j in [-128,127] -> three int8 A operands,
+//     W*S = 65536 a0 + 256 a1 + a2, a_j in [-128,127] -> three int8 B operands,
 //   * tcgen05.mma kind::i8 (s8 x s8 -> s32 accumulators in TMEM): |sum| <= 274*128*128 < 2^23, no overflow,
 //   * real part uses the byte stream as is, the imaginary part a second stream with every (I,Q) pair
-//     replaced by (Q, ~I)  (~I = -I'-1): sum a[2m]*Q' + a[2m+1]*(-I'-1) with the same A rows
+//     replaced by (Q, ~I)  (~I = -I'-1): sum a[2m]*Q' + a[2m+1]*(-I'-1) with the same template rows
 //     a[2m] = Re W, a[2m+1] = -Im W.
 //
-// The Toeplitz operand is never materialised per lag: an "expanded" tile P[u][r][16 B] = z[16u+2r ..+15]
-// is built once per 192-lag tile in shared memory (16x expansion of ~0.7 KB); block u is exactly the
-// 8-row x 16-byte K-major core matrix of (row group g, K chunk c) for every g+c = u, so one UMMA
-// shared-memory descriptor with LBO = SBO = 128 B addresses the whole Hankel tile.
+// Operand roles: the 128 LAGS of a sub-tile are the M dimension (TMEM lanes), the <= 96 TEMPLATES of a chunk
+// (3 PSS roots x <= 32 frequency hypotheses) the N dimension (TMEM columns).  With the lags on the lanes
+//   * all four warp schedulers of the SM share the epilogue evenly (each lane quarter carries lags),
+//   * a template's fold offset (its k_factor, searcher.cpp:298) is uniform across a warp: the read-modify-write
+//     of the incoherent sum touches 32 consecutive floats - conflict-free for any offset,
+//   * the per-template constants are warp-uniform operands.
 //
-// Per CTA (persistent, one per SM): warp 0 builds P tiles, warp 1 issues the MMAs (one elected
-// thread, 54 UTCIMMA per 32-lag sub-tile into a double-buffered set of 6 TMEM accumulators), warps
-// 2-5 read the accumulators back (tcgen05.ld), turn them into |xc|^2 and fold the 15 half frames
-// into per-template accumulators in shared memory with each template's own k_factor offset
-// (searcher.cpp:298).  Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
+// The Toeplitz (Hankel) A operand is never materialised per lag: an "expanded" tile P[u][r][16 B] = z[16u+2r ..+15]
+// is built once per 256-lag tile in shared memory (8x expansion of ~0.8 KB); block u is exactly the
+// 8-row x 16-byte K-major core matrix of (row group g, K chunk c) for every g+c = u, so one UMMA
+// shared-memory descriptor with LBO = SBO = 128 B addresses the whole Hankel tile.  The template digit planes
+// stay resident in shared memory in core-matrix order (LBO 128 B, SBO 2304 B).
+//
+// Per CTA (persistent, one per SM): warp 0 builds P tiles, warp 1 issues the MMAs (one elected lane, 9 UTCIMMA per
+// (sub-tile, re/im, digit) plane into a ring of 4 TMEM accumulator planes), warps 2-17 read the planes back
+// (tcgen05.ld), recombine the digits, turn them into |xc|^2 and fold the 15 half frames into per-template
+// accumulators in shared memory.  Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +42,9 @@
 #ifndef LCS_TC_PROFILE
 #define LCS_TC_PROFILE 0
 #endif
+#ifndef LCS_TC_DBG
+#define LCS_TC_DBG 0    // 1: honour TcParams::dbg (timing experiments that skip epilogue stages; wrong results)
+#endif
 #if LCS_TC_PROFILE
 #define TC_CLK() clock64()
 #else
@@ -45,55 +55,56 @@ namespace lcs {
 
 namespace tc {
 constexpr int NT = 256;            // lags per tile
-constexpr int NSUBL = 128;         // lags per MMA (UMMA N): one instruction costs max(N,128)/2 cycles (tools/microbench)
+constexpr int NSUBL = 128;         // lags per MMA (UMMA M)
 constexpr int NSUB = NT / NSUBL;   // MMA sub-tiles per tile
 constexpr int KB = 288;            // K in bytes: 274 interleaved I/Q taps padded to a multiple of 32
 constexpr int KSTEPS = KB / 32;    // UTCIMMA K = 32 bytes
+constexpr int KCHUNKS = KB / 16;   // 16-byte K chunks (core-matrix columns)
 constexpr int NBLK = NT / 8 + KB / 16 - 1;   // 49 expanded blocks of 128 B per tile
 constexpr int P_BYTES = NBLK * 128;          // one variant of one stage
-constexpr int A_ROW_WORDS = KB / 4;          // 72 TMEM columns per digit plane
-constexpr int A_TILE_BYTES = 128 * KB;       // one digit plane: 128 rows x 288 B = 36864
-constexpr int A_BYTES = 3 * A_TILE_BYTES;    // global: [3 digits][128 rows][288 B], row-major
-constexpr int POW_STRIDE = 255;    // == -1 (mod 32): with fold offsets that decrease along the rows the per-lane
-                                   // read-modify-write addresses of a warp fall into distinct banks
-constexpr int T_MAX = POW_STRIDE - 1;        // fold positions per tile (<= NT - spread)
-// Warp layouts.  COMPACT (3*n_f <= 96, TMEM lanes 96..127 hold padding rows): 16 warps; warp = colgrp*4 + quarter; the
-// quarter-3 warps have no rows to drain, so two of them are the P builder and the MMA issuer -> 128 registers/thread.
-// FULL: 2 service warps + 16 epilogue warps (18 warps -> 96 registers/thread).
-constexpr int THREADS_COMPACT = 512;
-constexpr int THREADS_FULL = 576;
-constexpr int NSLOT = 2;           // accumulator planes in flight
-constexpr int SMEM_P = 0;                                      // [2 stages][2 variants][P_BYTES]
-constexpr int SMEM_POW = SMEM_P + 4 * P_BYTES;                 // [128][POW_STRIDE] float
-constexpr int SMEM_BAR = SMEM_POW + 128 * POW_STRIDE * 4;      // 4 + 2*NSLOT mbarriers
-constexpr int SMEM_MISC = SMEM_BAR + 16 * 8;
-constexpr int RAW_CHUNKS = (2 * NT + KB + 16 + 15 + 15) / 16 + 1;   // 16-byte chunks of raw IQ bytes per tile (+ slack)
-constexpr int SMEM_RAW = SMEM_MISC + 16;
-constexpr int SMEM_TOTAL = SMEM_RAW + RAW_CHUNKS * 16 + 16;
-// TMEM map (512 columns): [0,216) the three int8 digit planes of the templates (A operand of the .ts MMA form: the
-// tensor core then reads only the Hankel tile from shared memory, half the operand traffic of the .ss form);
-// [256,512) two accumulator planes of 128 lags x int32 (one (digit, re/im) product each), used alternately.
+constexpr int N_MAX = 96;          // template columns per chunk (UMMA N, a multiple of 32): 32 hypotheses x 3 roots
+constexpr int F_CHUNK = N_MAX / 3;
+constexpr int B_SBO = KCHUNKS * 128;         // bytes between 8-template groups of one digit plane
+constexpr int POW_STRIDE = 256;    // floats per template row of the incoherent sum (lags on consecutive addresses)
+constexpr int M_MAX = 24;          // half frames whose per-template offsets fit the shared-memory table
+constexpr int THREADS = 576;       // P builder + MMA issuer + 16 epilogue warps
+constexpr int N_EPI_WARPS = 16;
+constexpr int NSLOT = 4;           // accumulator planes in flight (4 x 128 TMEM columns)
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_ACC0 = 256;
 constexpr uint32_t TMEM_SLOT = 128;
+constexpr int RAW_CHUNKS = (2 * NT + KB + 16 + 15 + 15) / 16 + 1;   // 16-byte chunks of raw IQ bytes per tile (+ slack)
+// shared-memory map for a chunk padded to npad template columns
+constexpr int SMEM_P = 0;                                      // [2 stages][2 variants][P_BYTES]
+constexpr int SMEM_B = SMEM_P + 4 * P_BYTES;                   // [3 digits][npad/8][KCHUNKS][8][16] int8
+__host__ __device__ constexpr int smem_pow(int npad) { return SMEM_B + 3 * (npad / 8) * B_SBO; }            // [npad][POW_STRIDE] float
+__host__ __device__ constexpr int smem_corr(int npad) { return smem_pow(npad) + npad * POW_STRIDE * 4; }    // [2][npad] float
+__host__ __device__ constexpr int smem_dsh(int npad) { return smem_corr(npad) + 2 * npad * 4; }             // [M_MAX][npad] int32 byte offsets
+__host__ __device__ constexpr int smem_bar(int npad) { return smem_dsh(npad) + M_MAX * npad * 4; }          // 4 + 2*NSLOT mbarriers
+__host__ __device__ constexpr int smem_misc(int npad) { return smem_bar(npad) + 16 * 8; }
+__host__ __device__ constexpr int smem_raw(int npad) { return smem_misc(npad) + 16; }
+__host__ __device__ constexpr int smem_total(int npad) { return smem_raw(npad) + RAW_CHUNKS * 16 + 16; }
 // UTCIMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) bits[4,6);
 // a_format / b_format = 1 (signed 8 bit) bits [7,10) / [10,13); K-major A and B; N>>3 bits [17,23); M>>4 bits [24,29)
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NSUBL >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc(int npad) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | ((128u >> 4) << 24);
+}
 }  // namespace tc
 
 struct TcParams {
   const uint8_t* iq;          // [batch][n_cap][2] raw bytes
-  const uint8_t* a_op;        // [3 digits][128 rows][288] int8, row-major
-  const int* soff;            // [n_comb][n_f]
+  const uint8_t* b_op;        // [3 digits][npad/8][KCHUNKS][8][16] int8 template digits in UMMA core-matrix order
+  const int16_t* dsh;         // [n_comb][npad] fold offset of the column's hypothesis minus the chunk minimum
   const int* smin_all;        // [n_comb] min over the chunk's f
-  const float* corr;          // [128][2] (C_re, C_im)
+  const int* dmax_all;        // [n_comb] max of dsh over the chunk's columns
+  const float* corr;          // [2][npad] (C_re row, C_im row)
   float* single_planar;       // [batch][3][n_f][9600]
-  uint32_t n_cap, n_f, n_comb, batch;   // n_f = hypotheses in this chunk (<= 42)
+  uint32_t n_cap, n_f, n_comb, batch;   // n_f = hypotheses in this chunk (<= 32)
   uint32_t f0, n_f_total;     // first hypothesis of the chunk / size of the whole grid
   uint32_t t_tile;            // fold positions per tile
   uint32_t tiles_per_buf;     // ceil(9600 / t_tile)
   float inv_scale;            // 1 / (S * 128)
   long long* prof;            // optional [grid][8] cycle counters (NULL = off)
+  uint32_t dbg;               // LCS_TC_DBG builds only: 1 = epilogue releases planes unread, 2 = no fold, 3 = read but no math (timing experiments, wrong results)
 };
 
 // ---- small PTX wrappers ----
@@ -201,66 +212,62 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-template <bool COMPACT>
-__device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
-  constexpr int NTHREADS = COMPACT ? tc::THREADS_COMPACT : tc::THREADS_FULL;
-  constexpr int N_EPI_WARPS = COMPACT ? 12 : 16;
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+// NC = template columns per epilogue warp (npad / 4): 8, 16 or 24
+template <int NC>
+__global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
+  constexpr int NPAD = 4 * NC;
+  constexpr int B_PLANE = (NPAD / 8) * tc::B_SBO;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // roles
-  const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31 are accessible to this warp
-  const int ewarp = COMPACT ? warp : warp - 2;                     // epilogue numbering
-  const int colgrp = ewarp >> 2;                                  // which 32 of the 128 sub-tile columns
-  const bool is_pbuilder = COMPACT ? (warp == 3) : (warp == 0);
-  const bool is_mma = COMPACT ? (warp == 7) : (warp == 1);
-  const bool is_epi = COMPACT ? (quarter != 3) : (warp >= 2);
+  const int quarter = warp & 3;                   // TMEM lanes 32*quarter .. +31 are accessible to this warp
+  const int ewarp = warp - 2;                     // epilogue numbering 0..15
+  const int colgrp = ewarp >> 2;                  // which NC of the chunk's template columns
   uint8_t* sP = smem + tc::SMEM_P;
-  float* sPow = reinterpret_cast<float*>(smem + tc::SMEM_POW);
-  const uint32_t bar0 = smem_u32(smem + tc::SMEM_BAR);
+  float* sPow = reinterpret_cast<float*>(smem + tc::smem_pow(NPAD));
+  float* sCorr = reinterpret_cast<float*>(smem + tc::smem_corr(NPAD));
+  int* sDoff = reinterpret_cast<int*>(smem + tc::smem_dsh(NPAD));
+  const uint32_t bar0 = smem_u32(smem + tc::smem_bar(NPAD));
   // barriers (8 B each): 0,1 p_full[stage]; 2,3 p_empty[stage]; 4.. acc_full[slot]; 4+NSLOT.. acc_empty[slot]
   const uint32_t BAR_PFULL = bar0, BAR_PEMPTY = bar0 + 16, BAR_AFULL = bar0 + 32, BAR_AEMPTY = bar0 + 32 + 8 * tc::NSLOT;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::SMEM_MISC);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::smem_misc(NPAD));
 
   // ---- one-time setup ----
-  for (int i = tid; i < 128 * tc::POW_STRIDE; i += NTHREADS) sPow[i] = 0.f;
+  for (int i = tid; i < NPAD * tc::POW_STRIDE; i += tc::THREADS) sPow[i] = 0.f;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.b_op);
+    uint4* dst = reinterpret_cast<uint4*>(smem + tc::SMEM_B);
+    for (int i = tid; i < 3 * B_PLANE / 16; i += tc::THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < 2 * NPAD; i += tc::THREADS) sCorr[i] = __ldg(p.corr + i);
+    for (int i = tid; i < (int)p.n_comb * NPAD; i += tc::THREADS) sDoff[i] = -4 * (int)p.dsh[i];
+  }
   if (tid == 0) {
     mbar_init(BAR_PFULL, 1); mbar_init(BAR_PFULL + 8, 1);
     mbar_init(BAR_PEMPTY, 1); mbar_init(BAR_PEMPTY + 8, 1);            // tcgen05.commit
-    for (int i = 0; i < tc::NSLOT; i++) { mbar_init(BAR_AFULL + 8 * i, 1); mbar_init(BAR_AEMPTY + 8 * i, N_EPI_WARPS); }
+    for (int i = 0; i < tc::NSLOT; i++) { mbar_init(BAR_AFULL + 8 * i, 1); mbar_init(BAR_AEMPTY + 8 * i, tc::N_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (is_mma) {  // TMEM allocation (whole warp), address lands in shared memory
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"(tc::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  fence_async_smem();      // template planes: generic-proxy stores -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 4 && warp < 8) {
-    // Template digit planes -> TMEM: lane = template row, 72 columns (288 int8) per digit.
-    const int row = quarter * 32 + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int j = 0; j < 3; j++) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.a_op + ((size_t)j * 128 + row) * tc::KB);
-      for (int c = 0; c < tc::A_ROW_WORDS / 8; c++) {
-        const uint4 lo = __ldg(src + 2 * c), hi = __ldg(src + 2 * c + 1);
-        const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        tmem_st8(tl + j * tc::A_ROW_WORDS + c * 8, v);
-      }
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   const uint32_t n_items = p.batch * p.tiles_per_buf;
   const uint32_t n_my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t n_tiles = n_my_items * p.n_comb;
 
-  if (is_pbuilder) {
+  if (warp == 0) {
     // ================= P builder =================
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
       const uint32_t item = blockIdx.x + (tc_i / p.n_comb) * gridDim.x, m = tc_i % p.n_comb;
@@ -270,10 +277,10 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       const int64_t z0 = 2 * ((int64_t)i0 + __ldg(p.smin_all + m));          // byte offset of the tile's first lag
       const uint8_t* zb = p.iq + (size_t)b * p.n_cap * 2;
       // Stage the tile's raw bytes (2*NT + KB + alignment slack < 1 KB) with coalesced 128-bit loads, then expand
-      // from shared memory: the expansion reads every byte 16 times, global memory only once.
+      // from shared memory: the expansion reads every byte 8 times, global memory only once.
       const int64_t zal = z0 & ~(int64_t)15;
       const int64_t zend = (int64_t)(p.batch - b) * p.n_cap * 2;              // bytes left in the whole allocation
-      uint4* raw = reinterpret_cast<uint4*>(smem + tc::SMEM_RAW);
+      uint4* raw = reinterpret_cast<uint4*>(smem + tc::smem_raw(NPAD));
       for (int c = lane; c < tc::RAW_CHUNKS; c += 32) {
         const int64_t a = zal + 16 * c;
         raw[c] = (a + 16 <= zend) ? __ldg(reinterpret_cast<const uint4*>(zb + a)) : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
@@ -306,10 +313,11 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_PFULL + 8 * stage);
     }
-  } else if (is_mma) {
+  } else if (warp == 1) {
     // ================= MMA issuer: the whole warp walks the pipeline convergently, one elected lane issues ====
-    const uint32_t sP_addr = smem_u32(sP);
+    const uint32_t sP_addr = smem_u32(sP), sB_addr = smem_u32(smem + tc::SMEM_B);
     const uint32_t flag = elect_one_flag();
+    constexpr uint32_t IDESC = tc::idesc(NPAD);
     // descriptors advance by adding to the 14-bit (address >> 4) field: +16 per 256-byte K step
     uint32_t jb = 0;   // running job counter: one job = one (sub-tile, re/im, digit) product into one accumulator plane
     long long t_pwait = 0, t_ewait = 0, t_start = TC_CLK();
@@ -323,7 +331,7 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       for (int q = 0; q < tc::NSUB; q++) {
 #pragma unroll 1
         for (int v = 0; v < 2; v++) {
-          const uint64_t b_desc = make_desc(sP_addr + (stage * 2 + v) * tc::P_BYTES + q * (tc::NSUBL / 8) * 128, 128, 128);
+          const uint64_t a_desc = make_desc(sP_addr + (stage * 2 + v) * tc::P_BYTES + q * (tc::NSUBL / 8) * 128, 128, 128);
 #pragma unroll
           for (int j = 0; j < 3; j++, jb++) {
             const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
@@ -331,10 +339,11 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
             mbar_wait(BAR_AEMPTY + 8 * slot, (suse & 1) ^ 1);      // epilogue drained this accumulator plane
             t_ewait += TC_CLK() - c0;
             tc_fence_after();
-            const uint32_t d = tmem_base + tc::TMEM_ACC0 + slot * tc::TMEM_SLOT;
+            const uint32_t d = tmem_base + slot * tc::TMEM_SLOT;
+            const uint64_t b_desc = make_desc(sB_addr + j * B_PLANE, 128, tc::B_SBO);
 #pragma unroll
             for (int s = 0; s < tc::KSTEPS; s++)
-              umma_i8_ts_g(flag, d, tmem_base + j * tc::A_ROW_WORDS + s * 8, b_desc + (uint64_t)(s * 16), tc::IDESC, s > 0);
+              umma_i8_g(flag, d, a_desc + (uint64_t)(s * 16), b_desc + (uint64_t)(s * 16), IDESC, s > 0);
             umma_commit_g(flag, BAR_AFULL + 8 * slot);              // plane ready
           }
         }
@@ -347,126 +356,135 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
       p.prof[blockIdx.x * 8 + 2] = t_ewait;
       p.prof[blockIdx.x * 8 + 3] = jb;
     }
-  } else if (is_epi) {
+  } else {
     // ================= epilogue: TMEM -> |xc|^2 -> fold =================
-    const int L = quarter * 32 + lane;              // template row
+    const int L = quarter * 32 + lane;              // lag row of the sub-tile
+    const int col0 = colgrp * NC;                   // first template column of this warp
     const uint32_t n_templ = 3 * p.n_f;
-    const bool valid = L < (int)n_templ;
-    const uint32_t f = valid ? L / 3 : 0;
-    const float2 c_re2 = make_float2(__ldg(p.corr + 2 * L), __ldg(p.corr + 2 * L));
-    const float2 c_im2 = make_float2(__ldg(p.corr + 2 * L + 1), __ldg(p.corr + 2 * L + 1));
     const float inv2s = p.inv_scale * p.inv_scale;  // inv_scale is a power of two: scaling commutes with the roundings
-    const float2 inv2 = make_float2(inv2s, inv2s), w256 = make_float2(256.f, 256.f);
-    float* myPow = sPow + L * tc::POW_STRIDE;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + tc::TMEM_ACC0 + colgrp * 32;
-    const bool warp_has_rows = COMPACT || (uint32_t)(quarter * 32) < n_templ;   // FULL layout: trailing quarters may be padding
-    uint32_t jb = 0;
+    char* myPowB = reinterpret_cast<char*>(sPow + col0 * tc::POW_STRIDE + L);
+    const float* cre = sCorr + col0;
+    const float* cim = sCorr + NPAD + col0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
+    const uint32_t dbg = LCS_TC_DBG ? p.dbg : 0;
     long long t_fwait = 0, t_ld = 0, e_start = TC_CLK();
+    // Drain accumulator plane k of the current fold (k = sub-tile*6 + re/im*3 + digit; 12 planes per fold walk the ring
+    // of 4 exactly three times, so slot and parity are compile-time functions of k and the fold's parity bit): this
+    // warp's 32 lags x NC templates go to registers, then the plane is released.
+    auto drain = [&](int (&dst)[NC], const int k, const uint32_t fold_par) {
+      const uint32_t slot = k & 3;
+      long long c0 = TC_CLK();
+      mbar_wait(BAR_AFULL + 8 * slot, (fold_par + (k >> 2)) & 1);
+      long long c1 = TC_CLK();
+      t_fwait += c1 - c0;
+      tc_fence_after();
+      const uint32_t src = lane_base + slot * tc::TMEM_SLOT;
+      if (dbg != 1) {
+        if (NC >= 16) tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&dst[0]));
+        if (NC == 8 || NC == 24) tmem_ld8(src + (NC - 8), *reinterpret_cast<int(*)[8]>(&dst[NC - 8]));
+        tmem_ld_wait();
+      }
+      t_ld += TC_CLK() - c1;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);   // plane is in registers
+    };
+    uint32_t fold_no = 0;       // folds processed by this CTA (each uses every ring slot three times)
     for (uint32_t it = 0; it < n_my_items; it++) {
       const uint32_t item = blockIdx.x + it * gridDim.x;
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
-      for (uint32_t m = 0; m < p.n_comb; m++) {
-        const int delta = valid ? __ldg(p.soff + m * p.n_f_total + p.f0 + f) - __ldg(p.smin_all + m) : 0;
+      for (uint32_t m = 0; m < p.n_comb; m++, fold_no++) {
+        const uint32_t fold_par = fold_no & 1;
+        const int dmax = __ldg(p.dmax_all + m);
+        const int* doff = sDoff + m * NPAD + col0;        // -4 * (fold offset of the column - chunk minimum), bytes
+#pragma unroll
         for (int q = 0; q < tc::NSUB; q++) {
-          if (!warp_has_rows) {            // padding rows: only keep the accumulator ring moving
-            for (int k = 0; k < 6; k++, jb++) {
-              const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
-              mbar_wait(BAR_AFULL + 8 * slot, suse & 1);
-              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);
-              __syncwarp();
-            }
-            continue;
-          }
           // Recombine the three digit planes: t = a0*256 + a1 (int32, exact), value = float(t)*256 + float(a2).
           // Planes arrive in the order (re: d0,d1,d2, im: d0,d1,d2); each is released as soon as it is in registers.
-          float2 RR[16];        // squared real parts, two columns per register pair
-          const int il0 = q * tc::NSUBL + colgrp * 32 - delta;
-          const bool inside = __all_sync(0xffffffffu, il0 >= 0 && il0 + 32 <= (int)p.t_tile);
+          int t[NC], a[NC];
+          float rr[NC];
+          if (dbg == 1 || dbg == 3) {
+            for (int k = 0; k < 6; k++) drain(t, q * 6 + k, fold_par);
+            if (dbg == 3 && t[0] == 0x7fffffff) sPow[0] = 1.f;
+            continue;
+          }
+          // ---- real part ----
+          drain(t, q * 6 + 0, fold_par);
+          drain(a, q * 6 + 1, fold_par);
 #pragma unroll
-          for (int v = 0; v < 2; v++) {
-            int t[32], a[32];
+          for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
+          drain(a, q * 6 + 2, fold_par);
 #pragma unroll
-            for (int j = 0; j < 3; j++, jb++) {
-              const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
-              long long c0 = TC_CLK();
-              mbar_wait(BAR_AFULL + 8 * slot, suse & 1);
-              long long c1 = TC_CLK();
-              t_fwait += c1 - c0;
-              tc_fence_after();
-              const uint32_t src = lane_base + slot * tc::TMEM_SLOT;
-              if (j == 0) {
-                tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&t[0]));
-                tmem_ld16(src + 16, *reinterpret_cast<int(*)[16]>(&t[16]));
-              } else {
-                tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&a[0]));
-                tmem_ld16(src + 16, *reinterpret_cast<int(*)[16]>(&a[16]));
-              }
-              tmem_ld_wait();
-              t_ld += TC_CLK() - c1;
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);   // plane is in registers
-              if (j == 1) {
+          for (int c = 0; c < NC; c += 4) {
+            const float4 k = *reinterpret_cast<const float4*>(cre + c);
+            const float kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
-                for (int c = 0; c < 32; c++) t[c] = t[c] * 256 + a[c];
-              }
+            for (int e = 0; e < 4; e++) {
+              const float x = __fadd_rn(__fmaf_rn((float)t[c + e], 256.f, (float)a[c + e]), kk[e]);
+              rr[c + e] = __fmul_rn(x, x);
             }
-            if (v == 0) {
+          }
+          // ---- imaginary part ----
+          drain(t, q * 6 + 3, fold_par);
+          drain(a, q * 6 + 4, fold_par);
 #pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                const float2 hi = make_float2((float)t[c], (float)t[c + 1]);
-                const float2 lo = make_float2((float)a[c], (float)a[c + 1]);
-                const float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), c_re2);
-                RR[c >> 1] = __fmul2_rn(x, x);
-              }
-            } else {
-              // IT++ sqr(complex<float>) (searcher.cpp:300): re*re+im*im un-fused; the power-of-two scale commutes.
-              // Fold in batches of 8 columns: 8 loads in flight, then 8 adds, then 8 stores.
+          for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
+          drain(a, q * 6 + 5, fold_par);
+          // this lane's lag inside the tile (before the column's fold offset) is q*128 + L
+          const bool inside = (q * tc::NSUBL + quarter * 32 - dmax >= 0) && (q * tc::NSUBL + quarter * 32 + 32 <= (int)p.t_tile);   // warp-uniform
+          // |xc|^2 = re^2 + im^2 (searcher.cpp:300), in the integer scale of the templates; the power-of-two scale
+          // factor is applied when the tile is written out.  rr[] becomes the tile's contribution to the fold.
 #pragma unroll
-              for (int c0 = 0; c0 < 32; c0 += 8) {
-                float pwv[8], cur[8];
+          for (int c = 0; c < NC; c += 4) {
+            const float4 k = *reinterpret_cast<const float4*>(cim + c);
+            const float kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                  const float2 hi = make_float2((float)t[c0 + c], (float)t[c0 + c + 1]);
-                  const float2 lo = make_float2((float)a[c0 + c], (float)a[c0 + c + 1]);
-                  float2 x = __fadd2_rn(__ffma2_rn(hi, w256, lo), c_im2);
-                  x = __fmul2_rn(x, x);
-                  const float2 pw = __fmul2_rn(__fadd2_rn(RR[(c0 + c) >> 1], x), inv2);
-                  pwv[c] = pw.x;
-                  pwv[c + 1] = pw.y;
-                }
-                float* dstp = myPow + il0 + c0;
-                if (inside) {
-#pragma unroll
-                  for (int c = 0; c < 8; c++) cur[c] = dstp[c];
-#pragma unroll
-                  for (int c = 0; c < 8; c++) dstp[c] = __fadd_rn(cur[c], pwv[c]);
-                } else {
-#pragma unroll
-                  for (int c = 0; c < 8; c++)
-                    if ((unsigned)(il0 + c0 + c) < p.t_tile) dstp[c] = __fadd_rn(dstp[c], pwv[c]);
-                }
-              }
+            for (int e = 0; e < 4; e++) {
+              const float x = __fadd_rn(__fmaf_rn((float)t[c + e], 256.f, (float)a[c + e]), kk[e]);
+              rr[c + e] = __fmaf_rn(x, x, rr[c + e]);
             }
+          }
+          // fold: all loads of the read-modify-write first (t[] is dead, its registers hold the addresses), then add + store
+          if (dbg == 2) {
+            if (rr[0] + rr[NC - 1] == 1.2345f) sPow[1] = 1.f;
+            continue;
+          }
+#pragma unroll
+          for (int c = 0; c < NC; c += 4) {
+            const int4 d4 = *reinterpret_cast<const int4*>(doff + c);
+            t[c] = d4.x; t[c + 1] = d4.y; t[c + 2] = d4.z; t[c + 3] = d4.w;
+          }
+          float cur[NC];
+          if (inside) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) cur[c] = *reinterpret_cast<const float*>(myPowB + t[c] + (c * tc::POW_STRIDE + q * tc::NSUBL) * 4);
+#pragma unroll
+            for (int c = 0; c < NC; c++) *reinterpret_cast<float*>(myPowB + t[c] + (c * tc::POW_STRIDE + q * tc::NSUBL) * 4) = __fadd_rn(cur[c], rr[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+              if ((unsigned)(q * tc::NSUBL * 4 + L * 4 + t[c]) < p.t_tile * 4) {
+                float* dst = reinterpret_cast<float*>(myPowB + t[c] + (c * tc::POW_STRIDE + q * tc::NSUBL) * 4);
+                *dst = __fadd_rn(*dst, rr[c]);
+              }
           }
         }
       }
       // ---- item done: write xc_incoherent_single rows (coalesced), reset the accumulators ----
-      epi_bar(32 * N_EPI_WARPS);
+      epi_bar(32 * tc::N_EPI_WARPS);
       const float ncf = (float)p.n_comb;
-      const uint32_t erank = COMPACT ? (uint32_t)(colgrp * 3 + quarter) : (uint32_t)ewarp;   // dense 0..N_EPI_WARPS-1
-      for (uint32_t row = erank; row < n_templ; row += N_EPI_WARPS) {
+      for (uint32_t row = ewarp; row < n_templ; row += tc::N_EPI_WARPS) {
         const uint32_t rf = row / 3, rt = row % 3;
         float* dst = p.single_planar + (((size_t)b * 3 + rt) * p.n_f_total + p.f0 + rf) * LCS_N_FOLD + i0;
         float* src = sPow + row * tc::POW_STRIDE;
         for (uint32_t i = lane; i < p.t_tile; i += 32) {
-          if (i0 + i < LCS_N_FOLD) dst[i] = __fdiv_rn(src[i], ncf);   // searcher.cpp:304
+          if (i0 + i < LCS_N_FOLD) dst[i] = __fdiv_rn(__fmul_rn(src[i], inv2s), ncf);   // searcher.cpp:304
           src[i] = 0.f;
         }
       }
-      epi_bar(32 * N_EPI_WARPS);
+      epi_bar(32 * tc::N_EPI_WARPS);
     }
-    if (LCS_TC_PROFILE && p.prof && lane == 0 && colgrp == 0 && quarter == 0) {
+    if (LCS_TC_PROFILE && p.prof && lane == 0 && ewarp == 0) {
       p.prof[blockIdx.x * 8 + 4] = TC_CLK() - e_start;
       p.prof[blockIdx.x * 8 + 5] = t_fwait;
       p.prof[blockIdx.x * 8 + 6] = t_ld;
@@ -476,26 +494,25 @@ __device__ __forceinline__ void xcorr_fold_tc_body(const TcParams& p) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (is_mma) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tc::TMEM_COLS));
   }
 }
 
-__global__ void __maxnreg__(128) xcorr_fold_tc_kernel_compact(const TcParams p) { xcorr_fold_tc_body<true>(p); }
-__global__ void __maxnreg__(96) xcorr_fold_tc_kernel_full(const TcParams p) { xcorr_fold_tc_body<false>(p); }
-
 // =============================================================================================
 // Host side
 // =============================================================================================
+static uint32_t tc_npad(uint32_t n_f_chunk) { return (3 * n_f_chunk + 31) / 32 * 32; }
+
 lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
   p->tc_ready = false;
   const XcorrGeom& g = p->geom;
-  // Hypotheses are processed in chunks of <= 42 (3*42 = 126 template rows of the 128-row M tile).
-  const uint32_t n_chunks = (g.n_f + 41) / 42;
+  // Hypotheses are processed in chunks of <= 32 (3*32 = 96 template columns of the UMMA N dimension).
+  const uint32_t n_chunks = (g.n_f + tc::F_CHUNK - 1) / tc::F_CHUNK;
   const uint32_t chunk = (g.n_f + n_chunks - 1) / n_chunks;
-  if (n_chunks > 8) return LCS_OK;
+  if (n_chunks > 8 || g.n_comb_xc > (uint32_t)tc::M_MAX) return LCS_OK;
   // fold-offset spread inside a chunk decides how many fold positions a 256-lag tile yields
-  std::vector<int> smin((size_t)n_chunks * g.n_comb_xc);
+  std::vector<int> smin((size_t)n_chunks * g.n_comb_xc), dmax((size_t)n_chunks * g.n_comb_xc);
   int spread = 0;
   for (uint32_t c = 0; c < n_chunks; c++)
     for (uint32_t m = 0; m < g.n_comb_xc; m++) {
@@ -505,10 +522,11 @@ lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
         hi = std::max(hi, p->h_soff[(size_t)m * g.n_f + f]);
       }
       smin[(size_t)c * g.n_comb_xc + m] = lo;
+      dmax[(size_t)c * g.n_comb_xc + m] = hi - lo;
       spread = std::max(spread, hi - lo);
     }
   if (spread > tc::NT - 64) return LCS_OK;         // grid too sparse for this tiling: the FP32 kernel handles it
-  const int t_tile = std::min(tc::T_MAX, tc::NT - spread);
+  const int t_tile = tc::NT - spread;
 
   // scale: power of two with |W*S| <= 127*65536 + 127*256 + 127
   double maxabs = 0;
@@ -518,50 +536,64 @@ lcs_status tc_plan_setup(lcs_xcorr_plan* p) {
   while (std::ldexp(maxabs, e) > limit) e--;
   const double S = std::ldexp(1.0, e);
 
-  std::vector<uint8_t> a_op((size_t)n_chunks * tc::A_BYTES, 0);
-  std::vector<float> corr((size_t)n_chunks * 256, 0.f);
+  // per chunk: digit planes in core-matrix order, corrections, fold-offset table (all sized for N_MAX columns)
+  constexpr size_t B_CHUNK_BYTES = (size_t)3 * (tc::N_MAX / 8) * tc::B_SBO;
+  std::vector<uint8_t> b_op(n_chunks * B_CHUNK_BYTES, 0);
+  std::vector<float> corr((size_t)n_chunks * 2 * tc::N_MAX, 0.f);
+  std::vector<int16_t> dsh((size_t)n_chunks * tc::M_MAX * tc::N_MAX, 0);
   for (uint32_t f = 0; f < g.n_f; f++) {
     const uint32_t c = f / chunk, fl = f - c * chunk;
-    uint8_t* ac = a_op.data() + (size_t)c * tc::A_BYTES;
-    auto put = [&](int row, int k, long long wint) {
+    const uint32_t npad = tc_npad(std::min(chunk, g.n_f - c * chunk));
+    const size_t plane = (size_t)(npad / 8) * tc::B_SBO;
+    uint8_t* bc = b_op.data() + c * B_CHUNK_BYTES;
+    auto put = [&](int col, int k, long long wint) {
       // balanced base-256 digits: wint = 65536 d0 + 256 d1 + d2, d1,d2 in [-128,127]
       long long d2 = ((wint % 256) + 256) % 256; if (d2 > 127) d2 -= 256;
       long long r1 = (wint - d2) / 256;
       long long d1 = ((r1 % 256) + 256) % 256; if (d1 > 127) d1 -= 256;
       long long d0 = (r1 - d1) / 256;
       const long long dig[3] = {d0, d1, d2};
-      for (int j = 0; j < 3; j++) ac[((size_t)j * 128 + row) * tc::KB + k] = (uint8_t)(int8_t)dig[j];   // row-major, goes to TMEM
+      // core matrix (column group col/8, K chunk k/16): 8 rows of 16 bytes
+      const size_t off = (size_t)(col / 8) * tc::B_SBO + (size_t)(k / 16) * 128 + (size_t)(col % 8) * 16 + (k % 16);
+      for (int j = 0; j < 3; j++) bc[j * plane + off] = (uint8_t)(int8_t)dig[j];
     };
     for (int t = 0; t < 3; t++) {
-      const int row = (int)fl * 3 + t;
+      const int col = (int)fl * 3 + t;
       long long sum_all = 0, sum_even = 0;
       for (int tap = 0; tap < 137; tap++) {
         const cd w = p->h_w[((size_t)f * 3 + t) * 137 + tap];
         const long long wr = std::llrint(w.real() * S), wi = std::llrint(w.imag() * S);
-        put(row, 2 * tap, wr);        // multiplies the I byte
-        put(row, 2 * tap + 1, -wi);   // multiplies the Q byte (re) / ~I byte (im)
+        put(col, 2 * tap, wr);        // multiplies the I byte
+        put(col, 2 * tap + 1, -wi);   // multiplies the Q byte (re) / ~I byte (im)
         sum_all += wr - wi;
         sum_even += wr;
       }
-      corr[(size_t)c * 256 + 2 * row] = (float)sum_all;       // x = x'+1 :  + sum_j a[j]
-      corr[(size_t)c * 256 + 2 * row + 1] = (float)sum_even;  // (Q', ~I') stream:  + sum_m a[2m]
+      corr[(size_t)c * 2 * tc::N_MAX + col] = (float)sum_all;           // x = x'+1 :  + sum_j a[j]
+      corr[(size_t)c * 2 * tc::N_MAX + npad + col] = (float)sum_even;   // (Q', ~I') stream:  + sum_m a[2m]
+      for (uint32_t m = 0; m < g.n_comb_xc; m++)
+        dsh[(size_t)c * tc::M_MAX * tc::N_MAX + (size_t)m * npad + col] = (int16_t)(p->h_soff[(size_t)m * g.n_f + f] - smin[(size_t)c * g.n_comb_xc + m]);
     }
   }
   lcs_ctx* ctx = p->ctx;
-  LCS_CUDA(ctx, p->d_tc_a.alloc(a_op.size()));
-  LCS_CUDA(ctx, p->d_tc_meta.alloc(smin.size()));
+  std::vector<int> meta(smin);
+  meta.insert(meta.end(), dmax.begin(), dmax.end());
+  LCS_CUDA(ctx, p->d_tc_a.alloc(b_op.size()));
+  LCS_CUDA(ctx, p->d_tc_meta.alloc(meta.size()));
   LCS_CUDA(ctx, p->d_tc_scale.alloc(corr.size()));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_a.p, a_op.data(), a_op.size(), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_meta.p, smin.data(), smin.size() * 4, cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, p->d_tc_dsh.alloc(dsh.size()));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_a.p, b_op.data(), b_op.size(), cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
   LCS_CUDA(ctx, cudaMemcpy(p->d_tc_scale.p, corr.data(), corr.size() * 4, cudaMemcpyHostToDevice));
+  LCS_CUDA(ctx, cudaMemcpy(p->d_tc_dsh.p, dsh.data(), dsh.size() * 2, cudaMemcpyHostToDevice));
   p->tc_params[0] = t_tile;
   p->tc_params[1] = (LCS_N_FOLD + t_tile - 1) / t_tile;
   float inv = (float)(1.0 / (S * 128.0));
   std::memcpy(&p->tc_params[2], &inv, 4);
   p->tc_params[3] = (int)n_chunks;
   p->tc_params[4] = (int)chunk;
-  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
-  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel_full, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_total(32)));
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_total(64)));
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::smem_total(96)));
   p->tc_ready = true;
   return LCS_OK;
 }
@@ -587,13 +619,15 @@ void tc_prof_dump() {
 
 int launch_xcorr_fold_tc(lcs_xcorr_plan* p, const void* d_iq_cu8, uint32_t batch, float* d_single_planar, cudaStream_t st) {
   const uint32_t n_chunks = (uint32_t)p->tc_params[3], chunk = (uint32_t)p->tc_params[4];
+  constexpr size_t B_CHUNK_BYTES = (size_t)3 * (tc::N_MAX / 8) * tc::B_SBO;
   for (uint32_t c = 0; c < n_chunks; c++) {
     TcParams q;
     q.iq = reinterpret_cast<const uint8_t*>(d_iq_cu8);
-    q.a_op = p->d_tc_a.p + (size_t)c * tc::A_BYTES;
-    q.soff = p->d_soff.p;
+    q.b_op = p->d_tc_a.p + c * B_CHUNK_BYTES;
+    q.dsh = p->d_tc_dsh.p + (size_t)c * tc::M_MAX * tc::N_MAX;
     q.smin_all = p->d_tc_meta.p + (size_t)c * p->geom.n_comb_xc;
-    q.corr = p->d_tc_scale.p + (size_t)c * 256;
+    q.dmax_all = p->d_tc_meta.p + (size_t)(n_chunks + c) * p->geom.n_comb_xc;
+    q.corr = p->d_tc_scale.p + (size_t)c * 2 * tc::N_MAX;
     q.single_planar = d_single_planar;
     q.n_cap = p->geom.n_cap;
     q.f0 = c * chunk;
@@ -605,10 +639,13 @@ int launch_xcorr_fold_tc(lcs_xcorr_plan* p, const void* d_iq_cu8, uint32_t batch
     q.tiles_per_buf = (uint32_t)p->tc_params[1];
     std::memcpy(&q.inv_scale, &p->tc_params[2], 4);
     q.prof = tc_prof_buffer();
+    q.dbg = std::getenv("LCS_TC_DBG") ? (uint32_t)std::atoi(std::getenv("LCS_TC_DBG")) : 0;
     const uint32_t n_items = batch * q.tiles_per_buf;
     const uint32_t grid = std::min<uint32_t>((uint32_t)p->ctx->n_sm, n_items);
-    if (3 * q.n_f <= 96) xcorr_fold_tc_kernel_compact<<<grid, tc::THREADS_COMPACT, tc::SMEM_TOTAL, st>>>(q);
-    else xcorr_fold_tc_kernel_full<<<grid, tc::THREADS_FULL, tc::SMEM_TOTAL, st>>>(q);
+    const uint32_t npad = tc_npad(q.n_f);
+    if (npad == 32) xcorr_fold_tc_kernel<8><<<grid, tc::THREADS, tc::smem_total(32), st>>>(q);
+    else if (npad == 64) xcorr_fold_tc_kernel<16><<<grid, tc::THREADS, tc::smem_total(64), st>>>(q);
+    else xcorr_fold_tc_kernel<24><<<grid, tc::THREADS, tc::smem_total(96), st>>>(q);
   }
   return (int)n_chunks;
 }

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblcs_b200.so")
+LIB_PATH = os.environ.get("LCS_B200_LIB") or os.path.join(HERE, "liblcs_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "lcs_b200.h")
 
 IQ_CF32, IQ_CU8, IQ_C128 = 0, 1, 2
