@@ -58,6 +58,16 @@ def f_alg(n_f, n_comb=15):
     return 8.0 * 137 * 3 * n_f * n_comb * 9600
 
 
+def ncu_traffic(kernel, capbufs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/traffic.json, bytes per capture buffer of the bench workload), scaled to this launch; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_capbuf"]) * capbufs
+    except Exception:  # noqa
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,12 +351,13 @@ def main():
         if kernel_used == "xcorr_fold_tc":
             roof = {"bound": "tensor", "achieved": alg_flops / k_avg_s / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "tensor_mode": "tcgen05 kind::i8 (s8 x s8 -> s32, exact); the driver measures only a bf16 peak, int8 runs at 2x "
-                                   "that rate; achieved counts F_alg only - the kernel executes 3 int8 digit planes x 128/93 row padding "
-                                   "x 288/274 K padding x 256/228 tile overlap = 4.9x more MACs than F_alg"}
+                                   "that rate; achieved counts F_alg only - the kernel executes 3 int8 digit planes x 96/93 column padding "
+                                   "x 288/274 K padding x 256/229 tile overlap = 3.65x more MACs than F_alg, so it runs at "
+                                   "~2.5 int8 POP/s of executed work"}
         else:
             roof = {"bound": "hbm", "achieved": alg_bytes / k_avg_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof.update({"traffic": None, "kernel": kernel_used, "kernel_avg_ms": k_avg_s * 1e3, "kernel_launches": kernel_n,
+        roof.update({"traffic": ncu_traffic(kernel_used, B), "kernel": kernel_used, "kernel_avg_ms": k_avg_s * 1e3, "kernel_launches": kernel_n,
                      "kernel_share_of_step": kernel_ms / ms, "alg_bytes_per_launch": alg_bytes,
                      "alg_flops_per_launch": alg_flops, "alg_tflops": alg_flops / k_avg_s / 1e12,
                      "peak_source": peaks["source"],

@@ -69,9 +69,12 @@ constexpr int POW_STRIDE = 256;    // floats per template row of the incoherent 
 constexpr int M_MAX = 24;          // half frames whose per-template offsets fit the shared-memory table
 constexpr int THREADS = 576;       // P builder + MMA issuer + 16 epilogue warps
 constexpr int N_EPI_WARPS = 16;
-constexpr int NSLOT = 4;           // accumulator planes in flight (4 x 128 TMEM columns)
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_SLOT = 128;
+// TMEM map: two "wide" accumulator slots of 192 columns at 0 and 192 (digit planes 0 and 1 side by side, one UTCIMMA with
+// N = 2*npad: an instruction costs max(N,128)/2 cycles, so stacking planes is cheaper than issuing them one by one), and
+// "narrow" slots of npad columns from 384 (digit plane 2): two when they fit (npad <= 64), else one.
+constexpr uint32_t TMEM_WIDE = 192;
+constexpr uint32_t TMEM_NARROW0 = 384;
 constexpr int RAW_CHUNKS = (2 * NT + KB + 16 + 15 + 15) / 16 + 1;   // 16-byte chunks of raw IQ bytes per tile (+ slack)
 // shared-memory map for a chunk padded to npad template columns
 constexpr int SMEM_P = 0;                                      // [2 stages][2 variants][P_BYTES]
@@ -79,14 +82,14 @@ constexpr int SMEM_B = SMEM_P + 4 * P_BYTES;                   // [3 digits][npa
 __host__ __device__ constexpr int smem_pow(int npad) { return SMEM_B + 3 * (npad / 8) * B_SBO; }            // [npad][POW_STRIDE] float
 __host__ __device__ constexpr int smem_corr(int npad) { return smem_pow(npad) + npad * POW_STRIDE * 4; }    // [2][npad] float
 __host__ __device__ constexpr int smem_dsh(int npad) { return smem_corr(npad) + 2 * npad * 4; }             // [M_MAX][npad] int32 byte offsets
-__host__ __device__ constexpr int smem_bar(int npad) { return smem_dsh(npad) + M_MAX * npad * 4; }          // 4 + 2*NSLOT mbarriers
+__host__ __device__ constexpr int smem_bar(int npad) { return smem_dsh(npad) + M_MAX * npad * 4; }          // 12 mbarriers
 __host__ __device__ constexpr int smem_misc(int npad) { return smem_bar(npad) + 16 * 8; }
-__host__ __device__ constexpr int smem_raw(int npad) { return smem_misc(npad) + 16; }
+__host__ __device__ constexpr int smem_raw(int npad) { return smem_misc(npad) + 16 + M_MAX * 4; }
 __host__ __device__ constexpr int smem_total(int npad) { return smem_raw(npad) + RAW_CHUNKS * 16 + 16; }
 // UTCIMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) bits[4,6);
 // a_format / b_format = 1 (signed 8 bit) bits [7,10) / [10,13); K-major A and B; N>>3 bits [17,23); M>>4 bits [24,29)
-__host__ __device__ constexpr uint32_t idesc(int npad) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 }  // namespace tc
 
@@ -232,9 +235,12 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
   float* sPow = reinterpret_cast<float*>(smem + tc::smem_pow(NPAD));
   float* sCorr = reinterpret_cast<float*>(smem + tc::smem_corr(NPAD));
   int* sDoff = reinterpret_cast<int*>(smem + tc::smem_dsh(NPAD));
+  int* sDmax = reinterpret_cast<int*>(smem + tc::smem_misc(NPAD) + 16);     // [M_MAX] max fold offset per half frame
   const uint32_t bar0 = smem_u32(smem + tc::smem_bar(NPAD));
-  // barriers (8 B each): 0,1 p_full[stage]; 2,3 p_empty[stage]; 4.. acc_full[slot]; 4+NSLOT.. acc_empty[slot]
-  const uint32_t BAR_PFULL = bar0, BAR_PEMPTY = bar0 + 16, BAR_AFULL = bar0 + 32, BAR_AEMPTY = bar0 + 32 + 8 * tc::NSLOT;
+  // barriers (8 B each): 0,1 p_full[stage]; 2,3 p_empty[stage]; 4,5 wide_full[slot]; 6,7 wide_empty[slot];
+  // 8,9 narrow_full[slot]; 10,11 narrow_empty[slot]
+  const uint32_t BAR_PFULL = bar0, BAR_PEMPTY = bar0 + 16, BAR_WFULL = bar0 + 32, BAR_WEMPTY = bar0 + 48, BAR_XFULL = bar0 + 64, BAR_XEMPTY = bar0 + 80;
+  constexpr int NX = NPAD <= 64 ? 2 : 1;      // narrow slots
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tc::smem_misc(NPAD));
 
   // ---- one-time setup ----
@@ -245,11 +251,15 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
     for (int i = tid; i < 3 * B_PLANE / 16; i += tc::THREADS) dst[i] = __ldg(src + i);
     for (int i = tid; i < 2 * NPAD; i += tc::THREADS) sCorr[i] = __ldg(p.corr + i);
     for (int i = tid; i < (int)p.n_comb * NPAD; i += tc::THREADS) sDoff[i] = -4 * (int)p.dsh[i];
+    for (int i = tid; i < (int)p.n_comb; i += tc::THREADS) sDmax[i] = __ldg(p.dmax_all + i);
   }
   if (tid == 0) {
     mbar_init(BAR_PFULL, 1); mbar_init(BAR_PFULL + 8, 1);
     mbar_init(BAR_PEMPTY, 1); mbar_init(BAR_PEMPTY + 8, 1);            // tcgen05.commit
-    for (int i = 0; i < tc::NSLOT; i++) { mbar_init(BAR_AFULL + 8 * i, 1); mbar_init(BAR_AEMPTY + 8 * i, tc::N_EPI_WARPS); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(BAR_WFULL + 8 * i, 1); mbar_init(BAR_WEMPTY + 8 * i, tc::N_EPI_WARPS);
+      mbar_init(BAR_XFULL + 8 * i, 1); mbar_init(BAR_XEMPTY + 8 * i, tc::N_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
@@ -274,6 +284,7 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
       const uint32_t stage = tc_i & 1, use = tc_i >> 1;
       mbar_wait(BAR_PEMPTY + 8 * stage, (use & 1) ^ 1);   // wait until the MMAs that read this stage retired
+      if (LCS_TC_DBG && (p.dbg == 4 || p.dbg == 5)) { __syncwarp(); if (lane == 0) mbar_arrive(BAR_PFULL + 8 * stage); continue; }   // timing experiment: no P tiles
       const int64_t z0 = 2 * ((int64_t)i0 + __ldg(p.smin_all + m));          // byte offset of the tile's first lag
       const uint8_t* zb = p.iq + (size_t)b * p.n_cap * 2;
       // Stage the tile's raw bytes (2*NT + KB + alignment slack < 1 KB) with coalesced 128-bit loads, then expand
@@ -317,9 +328,11 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
     // ================= MMA issuer: the whole warp walks the pipeline convergently, one elected lane issues ====
     const uint32_t sP_addr = smem_u32(sP), sB_addr = smem_u32(smem + tc::SMEM_B);
     const uint32_t flag = elect_one_flag();
-    constexpr uint32_t IDESC = tc::idesc(NPAD);
+    constexpr uint32_t IDESC_W = tc::idesc(2 * NPAD), IDESC_X = tc::idesc(NPAD);
     // descriptors advance by adding to the 14-bit (address >> 4) field: +16 per 256-byte K step
-    uint32_t jb = 0;   // running job counter: one job = one (sub-tile, re/im, digit) product into one accumulator plane
+    const uint64_t bw_desc = make_desc(sB_addr, 128, tc::B_SBO);                  // digit planes 0|1: 2*NPAD template rows
+    const uint64_t bx_desc = make_desc(sB_addr + 2 * B_PLANE, 128, tc::B_SBO);    // digit plane 2
+    uint32_t st = 0;   // running sub-tile counter: every sub-tile uses wide slot v for part v (re/im) once
     long long t_pwait = 0, t_ewait = 0, t_start = TC_CLK();
     for (uint32_t tc_i = 0; tc_i < n_tiles; tc_i++) {
       const uint32_t stage = tc_i & 1, use = tc_i >> 1;
@@ -328,24 +341,30 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
       t_pwait += TC_CLK() - c0;
       tc_fence_after();
 #pragma unroll 1
-      for (int q = 0; q < tc::NSUB; q++) {
-#pragma unroll 1
+      for (int q = 0; q < tc::NSUB; q++, st++) {
+#pragma unroll
         for (int v = 0; v < 2; v++) {
           const uint64_t a_desc = make_desc(sP_addr + (stage * 2 + v) * tc::P_BYTES + q * (tc::NSUBL / 8) * 128, 128, 128);
+          // wide job: slot v, used once per sub-tile
+          c0 = TC_CLK();
+          mbar_wait(BAR_WEMPTY + 8 * v, (st & 1) ^ 1);
+          t_ewait += TC_CLK() - c0;
+          tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 3; j++, jb++) {
-            const uint32_t slot = jb % tc::NSLOT, suse = jb / tc::NSLOT;
-            c0 = TC_CLK();
-            mbar_wait(BAR_AEMPTY + 8 * slot, (suse & 1) ^ 1);      // epilogue drained this accumulator plane
-            t_ewait += TC_CLK() - c0;
-            tc_fence_after();
-            const uint32_t d = tmem_base + slot * tc::TMEM_SLOT;
-            const uint64_t b_desc = make_desc(sB_addr + j * B_PLANE, 128, tc::B_SBO);
+          for (int s = 0; s < tc::KSTEPS; s++)
+            umma_i8_g(flag, tmem_base + v * tc::TMEM_WIDE, a_desc + (uint64_t)(s * 16), bw_desc + (uint64_t)(s * 16), IDESC_W, s > 0);
+          umma_commit_g(flag, BAR_WFULL + 8 * v);
+          // narrow job: NX == 2: slot v once per sub-tile; NX == 1: slot 0 twice per sub-tile
+          const uint32_t xs = NX == 2 ? v : 0;
+          const uint32_t xpar = NX == 2 ? (st & 1) : (uint32_t)v;
+          c0 = TC_CLK();
+          mbar_wait(BAR_XEMPTY + 8 * xs, xpar ^ 1);
+          t_ewait += TC_CLK() - c0;
+          tc_fence_after();
 #pragma unroll
-            for (int s = 0; s < tc::KSTEPS; s++)
-              umma_i8_g(flag, d, a_desc + (uint64_t)(s * 16), b_desc + (uint64_t)(s * 16), IDESC, s > 0);
-            umma_commit_g(flag, BAR_AFULL + 8 * slot);              // plane ready
-          }
+          for (int s = 0; s < tc::KSTEPS; s++)
+            umma_i8_g(flag, tmem_base + tc::TMEM_NARROW0 + xs * NPAD, a_desc + (uint64_t)(s * 16), bx_desc + (uint64_t)(s * 16), IDESC_X, s > 0);
+          umma_commit_g(flag, BAR_XFULL + 8 * xs);
         }
       }
       umma_commit_g(flag, BAR_PEMPTY + 8 * stage);                  // P stage free again
@@ -354,7 +373,7 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
       p.prof[blockIdx.x * 8 + 0] = TC_CLK() - t_start;
       p.prof[blockIdx.x * 8 + 1] = t_pwait;
       p.prof[blockIdx.x * 8 + 2] = t_ewait;
-      p.prof[blockIdx.x * 8 + 3] = jb;
+      p.prof[blockIdx.x * 8 + 3] = st;
     }
   } else {
     // ================= epilogue: TMEM -> |xc|^2 -> fold =================
@@ -365,55 +384,70 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
     char* myPowB = reinterpret_cast<char*>(sPow + col0 * tc::POW_STRIDE + L);
     const float* cre = sCorr + col0;
     const float* cim = sCorr + NPAD + col0;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
     const uint32_t dbg = LCS_TC_DBG ? p.dbg : 0;
     long long t_fwait = 0, t_ld = 0, e_start = TC_CLK();
-    // Drain accumulator plane k of the current fold (k = sub-tile*6 + re/im*3 + digit; 12 planes per fold walk the ring
-    // of 4 exactly three times, so slot and parity are compile-time functions of k and the fold's parity bit): this
-    // warp's 32 lags x NC templates go to registers, then the plane is released.
-    auto drain = [&](int (&dst)[NC], const int k, const uint32_t fold_par) {
-      const uint32_t slot = k & 3;
+    // Wide slot v (re/im) holds digit planes 0 and 1 of the current sub-tile, the narrow slot digit plane 2.  This warp's
+    // 32 lags x NC templates go to registers, then the slot is released.  Parities: the wide slots and (NX == 2) the narrow
+    // slots are used once per sub-tile, the single narrow slot (NX == 1) twice.
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
+    auto ld_cols = [&](uint32_t src, int (&dst)[NC]) {
+      if (NC >= 16) tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&dst[0]));
+      if (NC == 8 || NC == 24) tmem_ld8(src + (NC - 8), *reinterpret_cast<int(*)[8]>(&dst[NC - 8]));
+    };
+    auto drain_wide = [&](int (&d0)[NC], int (&d1)[NC], const int v, const uint32_t st_par) {
       long long c0 = TC_CLK();
-      mbar_wait(BAR_AFULL + 8 * slot, (fold_par + (k >> 2)) & 1);
+      mbar_wait(BAR_WFULL + 8 * v, st_par);
       long long c1 = TC_CLK();
       t_fwait += c1 - c0;
       tc_fence_after();
-      const uint32_t src = lane_base + slot * tc::TMEM_SLOT;
-      if (dbg != 1) {
-        if (NC >= 16) tmem_ld16(src, *reinterpret_cast<int(*)[16]>(&dst[0]));
-        if (NC == 8 || NC == 24) tmem_ld8(src + (NC - 8), *reinterpret_cast<int(*)[8]>(&dst[NC - 8]));
+      if (dbg != 1 && dbg != 5) {
+        ld_cols(lane_base + v * tc::TMEM_WIDE, d0);
+        ld_cols(lane_base + v * tc::TMEM_WIDE + NPAD, d1);
         tmem_ld_wait();
       }
       t_ld += TC_CLK() - c1;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR_AEMPTY + 8 * slot);   // plane is in registers
+      if (lane == 0) mbar_arrive(BAR_WEMPTY + 8 * v);
     };
-    uint32_t fold_no = 0;       // folds processed by this CTA (each uses every ring slot three times)
+    auto drain_narrow = [&](int (&d2)[NC], const int v, const uint32_t st_par) {
+      const uint32_t xs = NX == 2 ? v : 0;
+      long long c0 = TC_CLK();
+      mbar_wait(BAR_XFULL + 8 * xs, NX == 2 ? st_par : (uint32_t)v);
+      long long c1 = TC_CLK();
+      t_fwait += c1 - c0;
+      tc_fence_after();
+      if (dbg != 1 && dbg != 5) {
+        ld_cols(lane_base + tc::TMEM_NARROW0 + xs * NPAD, d2);
+        tmem_ld_wait();
+      }
+      t_ld += TC_CLK() - c1;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_XEMPTY + 8 * xs);
+    };
+    uint32_t st_par = 0;        // parity of the running sub-tile counter
     for (uint32_t it = 0; it < n_my_items; it++) {
       const uint32_t item = blockIdx.x + it * gridDim.x;
       const uint32_t b = item / p.tiles_per_buf, i0 = (item % p.tiles_per_buf) * p.t_tile;
-      for (uint32_t m = 0; m < p.n_comb; m++, fold_no++) {
-        const uint32_t fold_par = fold_no & 1;
-        const int dmax = __ldg(p.dmax_all + m);
+      for (uint32_t m = 0; m < p.n_comb; m++) {
+        const int dmax = sDmax[m];
         const int* doff = sDoff + m * NPAD + col0;        // -4 * (fold offset of the column - chunk minimum), bytes
 #pragma unroll
-        for (int q = 0; q < tc::NSUB; q++) {
+        for (int q = 0; q < tc::NSUB; q++, st_par ^= 1) {
           // Recombine the three digit planes: t = a0*256 + a1 (int32, exact), value = float(t)*256 + float(a2).
-          // Planes arrive in the order (re: d0,d1,d2, im: d0,d1,d2); each is released as soon as it is in registers.
           int t[NC], a[NC];
           float rr[NC];
-          if (dbg == 1 || dbg == 3) {
-            for (int k = 0; k < 6; k++) drain(t, q * 6 + k, fold_par);
+          if (dbg == 1 || dbg == 3 || dbg == 5) {
+            for (int v = 0; v < 2; v++) { drain_wide(t, a, v, st_par); drain_narrow(a, v, st_par); }
             if (dbg == 3 && t[0] == 0x7fffffff) sPow[0] = 1.f;
             continue;
           }
           // ---- real part ----
-          drain(t, q * 6 + 0, fold_par);
-          drain(a, q * 6 + 1, fold_par);
+          drain_wide(t, a, 0, st_par);
 #pragma unroll
           for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
-          drain(a, q * 6 + 2, fold_par);
+          drain_narrow(a, 0, st_par);
 #pragma unroll
           for (int c = 0; c < NC; c += 4) {
             const float4 k = *reinterpret_cast<const float4*>(cre + c);
@@ -425,13 +459,10 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
             }
           }
           // ---- imaginary part ----
-          drain(t, q * 6 + 3, fold_par);
-          drain(a, q * 6 + 4, fold_par);
+          drain_wide(t, a, 1, st_par);
 #pragma unroll
           for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
-          drain(a, q * 6 + 5, fold_par);
-          // this lane's lag inside the tile (before the column's fold offset) is q*128 + L
-          const bool inside = (q * tc::NSUBL + quarter * 32 - dmax >= 0) && (q * tc::NSUBL + quarter * 32 + 32 <= (int)p.t_tile);   // warp-uniform
+          drain_narrow(a, 1, st_par);
           // |xc|^2 = re^2 + im^2 (searcher.cpp:300), in the integer scale of the templates; the power-of-two scale
           // factor is applied when the tile is written out.  rr[] becomes the tile's contribution to the fold.
 #pragma unroll
@@ -454,6 +485,8 @@ __global__ void __maxnreg__(96) xcorr_fold_tc_kernel(const TcParams p) {
             const int4 d4 = *reinterpret_cast<const int4*>(doff + c);
             t[c] = d4.x; t[c + 1] = d4.y; t[c + 2] = d4.z; t[c + 3] = d4.w;
           }
+          // this lane's lag inside the tile (before the column's fold offset) is q*128 + L
+          const bool inside = (q * tc::NSUBL + quarter * 32 - dmax >= 0) && (q * tc::NSUBL + quarter * 32 + 32 <= (int)p.t_tile);   // warp-uniform
           float cur[NC];
           if (inside) {
 #pragma unroll
