@@ -342,6 +342,24 @@ def main():
     h2d = B * N_CAP * 2
     d2h = B * out_bytes_per_cap
 
+    # ---- e2e_search: the same host buffers through the batched search call (xcorr_pss + threshold + peak_search on the
+    # device, per-peak stages for buffers with a PSS; only cells return) - what a sweep / tracker actually consumes ----
+    def search_step():
+        return plan.cell_search_batch_cu8(None, max_cells=8, host_ptr=h_iq.data_ptr(), batch=B)
+
+    for _ in range(2):
+        search_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_found = 0
+    for _ in range(e2e_steps):
+        n_found += sum(len(c) for c in search_step())
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    search_val = world * B * e2e_steps / float(t.item()) * N_CAP / 1e6
+
     if rank == 0:
         peaks = load_peaks()
         k_avg_s = (kernel_ms / 1e3) / max(kernel_n, 1)
@@ -375,6 +393,10 @@ def main():
                        "kernel": kernel_used},
             "e2e": {"value": e2e_val, "unit": "Msamp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "lcs_xcorr_pss_batch_host (pinned host cu8 -> host pow/frq/sp_incoherent/single)"},
+            "e2e_search": {"value": search_val, "unit": "Msamp/s", "capbufs_per_s": search_val * 1e6 / N_CAP,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (4 + 32 * 24), "cells_found": n_found,
+                           "api": "lcs_cell_search_batch_cu8 (pinned host cu8 -> cells; xcorr_pss + Z_th1 + peak_search on the "
+                                  "device, xc_incoherent_single stays in HBM)"},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

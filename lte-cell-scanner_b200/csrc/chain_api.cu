@@ -41,12 +41,52 @@ static std::vector<cd> from_colmajor(const double* in, int n_rows, int n_cols) {
   return r;
 }
 
+// Per-peak stages of CellSearch.cpp:510-558 (sss_detect -> pss_sss_foe -> extract_tfg -> tfoec -> decode_mib) on a
+// device-resident capture buffer; cells that fail the SSS or MIB tests are dropped like in the reference.
+lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
+                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells) {
+  const double THRESH2_N_SIGMA = 3;     // CellSearch.cpp:528
+  lcs_status rc = LCS_OK;
+  if (pk.empty()) {
+    if (n_cells) *n_cells = 0;
+    return LCS_OK;
+  }
+  ChainScratch& cs = chain_scratch(ctx);
+  uint32_t found = 0;
+  for (lcs_cell c : pk) {
+    lcs_cell o;
+    rc = dev_sss_detect(ctx, cs, d_cap, fmt, n_cap, c, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, o, nullptr);
+    if (rc == LCS_ERR_RANGE) continue;   // the reference would index outside the buffer here
+    if (rc != LCS_OK) return rc;
+    if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
+    c = o;
+    rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
+    if (rc != LCS_OK) return rc;
+    c = o;
+    std::vector<cd> tfg, tfg_comp;
+    std::vector<double> ts, ts_comp;
+    rc = dev_extract_tfg(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, tfg, ts);
+    if (rc == LCS_ERR_RANGE) continue;
+    if (rc != LCS_OK) return rc;
+    RsDl rs(c.n_id_2 + 3 * c.n_id_1, c.cp_type);  // CellSearch.cpp:545
+    tfg_comp.resize(tfg.size());
+    ts_comp.resize(ts.size());
+    tfoec(c, tfg.data(), ts.data(), (int)ts.size(), fc_req, fc_prog, rs, tfg_comp.data(), ts_comp.data(), o);
+    c = o;
+    decode_mib(c, tfg_comp.data(), (int)ts.size(), rs, o);
+    if (o.n_rb_dl == -1) continue;  // CellSearch.cpp:554-558
+    if (found < max_cells && cells) cells[found] = o;
+    found++;
+  }
+  if (n_cells) *n_cells = found;
+  return LCS_OK;
+}
+
 // The chain of CellSearch.cpp:497-558 on a device-resident capture buffer.
 static lcs_status cell_search_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const double* f_search_set,
                                   uint32_t n_f, double fc_req, double fc_prog, double fs_prog, lcs_cell* cells,
                                   uint32_t max_cells, uint32_t* n_cells, lcs_cell* peaks, uint32_t* n_peaks) {
   const uint8_t DS_COMB_ARM = 2;        // CellSearch.cpp:484
-  const double THRESH2_N_SIGMA = 3;     // CellSearch.cpp:528
   lcs_xcorr_plan* p = nullptr;
   lcs_status rc = get_cached_plan(ctx, n_cap, f_search_set, n_f, DS_COMB_ARM, fc_req, fc_prog, fs_prog, &p);
   if (rc != LCS_OK) return rc;
@@ -79,35 +119,7 @@ static lcs_status cell_search_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint
   if (n_peaks) *n_peaks = (uint32_t)pk.size();
   if (peaks)
     for (size_t i = 0; i < pk.size() && i < max_cells; i++) peaks[i] = pk[i];
-  ChainScratch& cs = chain_scratch(ctx);
-  uint32_t found = 0;
-  for (lcs_cell c : pk) {
-    lcs_cell o;
-    rc = dev_sss_detect(ctx, cs, d_cap, fmt, n_cap, c, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, o, nullptr);
-    if (rc == LCS_ERR_RANGE) continue;   // the reference would index outside the buffer here
-    if (rc != LCS_OK) return rc;
-    if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
-    c = o;
-    rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
-    if (rc != LCS_OK) return rc;
-    c = o;
-    std::vector<cd> tfg, tfg_comp;
-    std::vector<double> ts, ts_comp;
-    rc = dev_extract_tfg(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, tfg, ts);
-    if (rc == LCS_ERR_RANGE) continue;
-    if (rc != LCS_OK) return rc;
-    RsDl rs(c.n_id_2 + 3 * c.n_id_1, c.cp_type);  // CellSearch.cpp:545
-    tfg_comp.resize(tfg.size());
-    ts_comp.resize(ts.size());
-    tfoec(c, tfg.data(), ts.data(), (int)ts.size(), fc_req, fc_prog, rs, tfg_comp.data(), ts_comp.data(), o);
-    c = o;
-    decode_mib(c, tfg_comp.data(), (int)ts.size(), rs, o);
-    if (o.n_rb_dl == -1) continue;  // CellSearch.cpp:554-558
-    if (found < max_cells && cells) cells[found] = o;
-    found++;
-  }
-  if (n_cells) *n_cells = found;
-  return LCS_OK;
+  return cell_chain_dev(ctx, d_cap, fmt, n_cap, pk, fc_req, fc_prog, fs_prog, cells, max_cells, n_cells);
 }
 
 }  // namespace lcs

@@ -44,6 +44,7 @@ void peak_search(const double* pow_in, const int32_t* frq, const double* z_th1, 
       if (row[c] > best) { best = row[c]; best_row = r; best_col = c; }
     }
     if (best < z_th1[best_col]) break;  // :446
+    if (!(best > 0)) break;             // all-zero input: the reference's loop would never end (0 < 0 is false)
     const int fi = frq[(size_t)best_row * LCS_N_FOLD + best_col];
     // refine the index inside +-arm (:457-465).  The reference iterates with a uint16 that wraps when
     // peak_ind < arm, in which case its loop body never runs and ind stays -1; reproduce that.

@@ -74,6 +74,10 @@ struct lcs_xcorr_plan {
     lcs::DevBuf<float> single;
     lcs::DevBuf<double> pow, spi, sp_partial;
     lcs::DevBuf<int32_t> frq;
+    // device peak search (search_batch.cu)
+    lcs::DevBuf<double> work;
+    lcs::DevBuf<unsigned char> peaks;
+    lcs::DevBuf<int32_t> npeaks;
   } hb[2];
 };
 
@@ -90,6 +94,8 @@ lcs_status fail(lcs_ctx* ctx, lcs_status st, const std::string& msg);
 lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_set, uint32_t n_f, uint8_t arm,
                            double fc_req, double fc_prog, double fs_prog, lcs_xcorr_plan** out);
 void chain_scratch_release(lcs_ctx* ctx);   // chain_api.cu
+lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
+                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells);   // chain_api.cu
 // xcorr_tc.cu
 lcs_status tc_plan_setup(lcs_xcorr_plan* p);
 void tc_prof_dump();

@@ -318,6 +318,29 @@ class XcorrPlan:
                       frq.ctypes.data, spi.ctypes.data)
         return dict(single=single, pow=pw, frq=frq, sp_incoherent=spi)
 
+    def peaks_batch(self, iq, iq_format, max_peaks=32, host_ptr=None, batch=None):
+        """xcorr_pss + threshold + peak_search on the device for a batch of host buffers (iq [batch][n_cap] in iq_format,
+        or a raw host pointer + batch).  Returns a list (per buffer) of lists of PSS-peak Cells."""
+        if host_ptr is None:
+            iq = np.ascontiguousarray(iq)
+            host_ptr, batch = iq.ctypes.data, iq.shape[0]
+        peaks = (Cell * (batch * max_peaks))()
+        n = (C.c_uint32 * batch)()
+        _chk(lib().lcs_xcorr_peaks_batch_host(self._h, C.c_void_p(host_ptr), int(iq_format), C.c_uint32(batch), peaks,
+                                              C.c_uint32(max_peaks), n), self.ctx._h)
+        return [[_copy(peaks[b * max_peaks + k]) for k in range(min(n[b], max_peaks))] for b in range(batch)]
+
+    def cell_search_batch_cu8(self, iq_cu8, max_cells=16, host_ptr=None, batch=None):
+        """The whole CellSearch chain for every buffer of a batch of raw rtl-sdr byte buffers (uint8 [batch][n_cap][2])."""
+        if host_ptr is None:
+            iq_cu8 = np.ascontiguousarray(iq_cu8, np.uint8)
+            host_ptr, batch = iq_cu8.ctypes.data, iq_cu8.shape[0]
+        cells = (Cell * (batch * max_cells))()
+        n = (C.c_uint32 * batch)()
+        _chk(lib().lcs_cell_search_batch_cu8(self._h, C.c_void_p(host_ptr), C.c_uint32(batch), cells, C.c_uint32(max_cells), n),
+             self.ctx._h)
+        return [[_copy(cells[b * max_cells + k]) for k in range(min(n[b], max_cells))] for b in range(batch)]
+
 
 def declared_symbols():
     """Function names declared in include/lcs_b200.h (for the export test)."""

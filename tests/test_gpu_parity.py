@@ -311,3 +311,61 @@ def test_tc_matches_fp32_kernel_and_auto_selection(ctx, lcs):
         plan.close()
     assert np.abs(outs[lcs.KERNEL_TC]["single"] - outs[lcs.KERNEL_FP32]["single"]).max() < 1e-6 * outs[lcs.KERNEL_FP32]["single"].max()
     assert (outs[lcs.KERNEL_TC]["frq"] != outs[lcs.KERNEL_FP32]["frq"]).mean() < 0.002
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side threshold + peak_search, batched search
+# ---------------------------------------------------------------------------------------------
+def _host_peaks(ctx, lcs, plan, cu8, f, fc):
+    """xcorr_pss through the plan, then threshold + peak_search with the HOST implementation (lcs_peak_search)."""
+    out = plan.run_host_np(cu8[None], lcs.IQ_CU8)
+    z = lcs.calc_z_th1(out["sp_incoherent"][0], plan.n_comb_xc, 2)
+    return lcs.peak_search(out["pow"][0], out["frq"][0], z, f, fc, fc, out["single"][0], 2)
+
+
+def test_device_peak_search_matches_host(ctx, lcs, capbuf0000):
+    """Device peak_search kernel == host peak_search (searcher.cpp:422-510) on the same device-computed pow/frq:
+    real capture (several peaks incl. ghost cancellation), noise (none), the same capture rolled so that a peak sits
+    at column < arm (the reference's uint16 wrap), and an all-equal buffer (zero power everywhere: the reference's loop
+    would not terminate there, both implementations stop)."""
+    fc = capbuf0000["fc"]
+    f = lcs.f_search_set(fc, 120.0)
+    real = capbuf0000["cu8"]
+    plan = ctx.plan(real.shape[0], f, 2, fc, fc, 1.92e6, max_batch=8)
+    ref0 = _host_peaks(ctx, lcs, plan, real, f, fc)
+    assert len(ref0) >= 2
+    rolled = np.roll(real, -(ref0[0].ind - 1), axis=0)          # strongest peak to fold position 1
+    bufs = [real, synth_cu8(0xC0FFEE), rolled, np.full_like(real, 127), synth_cu8(3, sigma=3.0)]
+    got = plan.peaks_batch(np.stack(bufs), lcs.IQ_CU8)
+    n_wrapped = 0
+    for b, cu8 in enumerate(bufs):
+        ref = _host_peaks(ctx, lcs, plan, cu8, f, fc)
+        assert [(p.n_id_2, p.ind, p.freq, p.pss_pow) for p in got[b]] == [(p.n_id_2, p.ind, p.freq, p.pss_pow) for p in ref], b
+        n_wrapped += sum(p.ind == -1 for p in ref)
+        for p in got[b]:
+            assert p.fc_requested == fc and p.fc_programmed == fc and p.n_id_1 == -1
+    assert len(got[1]) == 0 and len(got[3]) == 0
+    plan.close()
+
+
+def test_cell_search_batch_matches_single(ctx, lcs, capbuf0000):
+    """lcs_cell_search_batch_cu8 == lcs_cell_search_cu8 per buffer (cells 277/271 on the real capture, none on noise);
+    more buffers than one chunk so that both streams and the chunk hand-over are exercised."""
+    fc = capbuf0000["fc"]
+    f = lcs.f_search_set(fc, 120.0)
+    real = capbuf0000["cu8"]
+    order = [0, 1, 1, 0] + [1] * 31 + [0, 1]
+    noise = synth_cu8(0xBEEF)
+    bufs = np.stack([real if k == 0 else noise for k in order])
+    plan = ctx.plan(real.shape[0], f, 2, fc, fc, 1.92e6, max_batch=32)
+    got = plan.cell_search_batch_cu8(bufs)
+    ref_cells, _ = ctx.cell_search(real, f, fc, fc, 1.92e6)
+    assert [c.n_id_cell() for c in ref_cells] == [277, 271]
+    for k, cells in zip(order, got):
+        if k == 1:
+            assert cells == []
+            continue
+        assert len(cells) == len(ref_cells)
+        for a, b in zip(cells, ref_cells):
+            assert a.as_dict() == b.as_dict()
+    plan.close()
