@@ -165,6 +165,9 @@ def host_threads():
     return max(1, n)
 
 
+WORKLOAD = "xcorr_pss 153600-sample capbuf, n_f=31 (+-100 ppm @739 MHz), 3 PSS roots, ds_comb_arm=2"
+
+
 def run_reference(args):
     """--impl reference: the CPU oracle (HEAD-faithful port of searcher.cpp:113-383, OpenMP over
     the lag index like searcher.cpp:153) on this box's host cores.  The reference binary itself
@@ -230,6 +233,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="search", choices=["search", "tracker"],
+                    help="search: BASELINE configs[1] (n_f=31); tracker: SURVEY 8d config 5 shape (n_f=1 at the tracked offset)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -251,9 +256,11 @@ def main():
         os.environ["NCCL_DEBUG"] = os.environ.get("LCS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    f = f_grid()
+    f = f_grid() if args.workload == "search" else np.array([0.0])      # searcher_thread.cpp:97-98: one offset
     n_f = int(f.size)
     B = args.batch
+    wl_name = WORKLOAD if args.workload == "search" else ("tracker shape (SURVEY 8d config 5): xcorr_pss 153600-sample capbuf, n_f=1, "
+                                                          "3 PSS roots, ds_comb_arm=2; real time = 12.5 capbufs/s per channel")
     ctx = L.Context(local)
     kern = {"auto": L.KERNEL_AUTO, "fp32": L.KERNEL_FP32, "tc": L.KERNEL_TC}[args.kernel]
     plan = ctx.plan(N_CAP, f, ARM, FC, FC, FS, max_batch=B, kernel=kern)
@@ -386,11 +393,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kernel_used == "xcorr_fold_fp32" else "s8 (3 exact int8 digits, int32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": "xcorr_pss 153600-sample capbuf, n_f=31 (+-100 ppm @739 MHz), 3 PSS roots, ds_comb_arm=2",
+            "config": {"workload": wl_name,
                        "capbufs_per_step_per_gpu": B, "capbufs_per_s": capbufs_per_s, "n_f": n_f, "iq_format": "cu8",
                        "parallelism": "capbufs sharded across %d rank(s), no data-path collective" % world,
                        "l2": "ring of %d input/output sets (%.0f MB) larger than L2" % (ring, ring * B * (out_bytes_per_cap + N_CAP * 2) / 1e6),
-                       "kernel": kernel_used},
+                       "kernel": kernel_used,
+                       **({"realtime_channels": capbufs_per_s / 12.5} if args.workload == "tracker" else {})},
             "e2e": {"value": e2e_val, "unit": "Msamp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "lcs_xcorr_pss_batch_host (pinned host cu8 -> host pow/frq/sp_incoherent/single)"},
             "e2e_search": {"value": search_val, "unit": "Msamp/s", "capbufs_per_s": search_val * 1e6 / N_CAP,

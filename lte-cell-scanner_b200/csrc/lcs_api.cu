@@ -49,7 +49,8 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
   const uint32_t n_lag = n_cap - 136;
   g.n_comb_xc = (n_lag - 100) / LCS_N_FOLD;      // searcher.cpp:276
   g.n_comb_sp = (n_cap - 136 - 137) / LCS_N_FOLD;  // searcher.cpp:194
-  g.n_fchunk = (n_f + XC_FW - 1) / XC_FW;
+  g.fw = n_f == 1 ? 1 : XC_FW;                    // searcher_thread.cpp:97-98 searches a single offset
+  g.n_fchunk = (n_f + g.fw - 1) / g.fw;
 
   // Templates: conj(fshift(pss_td[t], f_off, fs_programmed*k_factor))/137  (searcher.cpp:145-151),
   // computed in double exactly like dsp.h:40-53 (cos/sin of k*t) and rounded once to fp32.
@@ -87,7 +88,7 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
   for (uint32_t m = 0; m < g.n_comb_xc; m++)
     for (uint32_t c = 0; c < g.n_fchunk; c++) {
       int lo = INT32_MAX, hi = INT32_MIN;
-      for (uint32_t f = c * XC_FW; f < std::min(n_f, (c + 1) * XC_FW); f++) {
+      for (uint32_t f = c * g.fw; f < std::min(n_f, (c + 1) * g.fw); f++) {
         lo = std::min(lo, soff[(size_t)m * n_f + f]);
         hi = std::max(hi, soff[(size_t)m * n_f + f]);
       }
@@ -95,8 +96,8 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
       max_spread = std::max(max_spread, (uint32_t)(hi - lo));
     }
   g.max_spread = max_spread;
-  g.tile_len = XC_TI + XC_NTAP_PAD + max_spread + 8;
-  const size_t smem = (size_t)XC_FW * XC_NTAP_PAD * 24 + (size_t)g.tile_len * 8;
+  g.tile_len = XC_TI * (XC_FW / g.fw) + XC_NTAP_PAD + max_spread + 8;
+  const size_t smem = (size_t)g.fw * XC_NTAP_PAD * 24 + (size_t)g.tile_len * 8;
   if (smem > 100 * 1024)
     return fail(ctx, LCS_ERR_RANGE, "xcorr plan: frequency grid too sparse for one shared-memory tile (spread too large)");
 

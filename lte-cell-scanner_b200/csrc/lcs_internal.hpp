@@ -16,12 +16,13 @@ typedef std::complex<double> cd;
 // ---- geometry of the fused FP32 correlator (xcorr_fp32.cu) ----
 constexpr int XC_R = 7;                 // lags per lane (7*8 B stride is LDS.64 bank-conflict free)
 constexpr int XC_TI = 32 * XC_R;        // 224 fold positions per block
-constexpr int XC_FW = 8;                // frequency hypotheses (warps) per block
+constexpr int XC_FW = 8;                // warps per block: fw frequency hypotheses x (8/fw) lag sub-tiles, fw = 8 or 1
 constexpr int XC_NTAP_PAD = 140;        // 137 taps zero-padded to a multiple of XC_R
 constexpr int XC_THREADS = 32 * XC_FW;
 
 struct XcorrGeom {
   uint32_t n_cap, n_f, n_comb_xc, n_comb_sp, n_fchunk, ds_comb_arm;
+  uint32_t fw;              // hypotheses per block of the FP32 correlator: 8, or 1 for the single-hypothesis (tracker) shape
   uint32_t tile_len;        // staged samples per (block, half-frame)
   uint32_t max_spread;
 };

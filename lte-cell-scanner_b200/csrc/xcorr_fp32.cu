@@ -60,7 +60,7 @@ __device__ __forceinline__ void cmac(float2& acc, const float wx, const float wy
   acc.y = fmaf(wy, x.x, acc.y);
 }
 
-template <int FMT>
+template <int FMT, int FW>
 __global__ void __launch_bounds__(XC_THREADS, 2)
 xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w01g, const float2* __restrict__ w2g,
                        const int* __restrict__ soff, const int* __restrict__ smin_tab, float* __restrict__ single_planar,
@@ -68,20 +68,23 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
                        const uint32_t tile_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* w01s = reinterpret_cast<float4*>(smem_raw);                        // [FW][NTAP_PAD] roots 0,1
-  float2* w2s = reinterpret_cast<float2*>(w01s + XC_FW * XC_NTAP_PAD);       // [FW][NTAP_PAD] root 2
-  float2* tile = w2s + XC_FW * XC_NTAP_PAD;                                  // [tile_len]
+  float2* w2s = reinterpret_cast<float2*>(w01s + FW * XC_NTAP_PAD);          // [FW][NTAP_PAD] root 2
+  float2* tile = w2s + FW * XC_NTAP_PAD;                                     // [tile_len]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t fchunk = blockIdx.y, b = blockIdx.z;
-  const uint32_t f = fchunk * XC_FW + warp;
+  // warp -> (hypothesis fsub of the chunk, lag sub-tile lsub of the block)
+  const int fsub = warp % FW, lsub = warp / FW;
+  const uint32_t f = fchunk * FW + fsub;
   const bool f_ok = f < n_f;
   const uint32_t fcl = f_ok ? f : n_f - 1;
-  const uint32_t i0 = blockIdx.x * XC_TI;
+  const uint32_t i0_blk = blockIdx.x * (XC_TI * (XC_FW / FW));
+  const uint32_t i0 = i0_blk + lsub * XC_TI;
   const size_t iq_base = (size_t)b * n_cap;
 
-  for (int i = tid; i < XC_FW * XC_NTAP_PAD; i += XC_THREADS) {
+  for (int i = tid; i < FW * XC_NTAP_PAD; i += XC_THREADS) {
     const uint32_t fw = i / XC_NTAP_PAD, tap = i - fw * XC_NTAP_PAD;
-    uint32_t ff = fchunk * XC_FW + fw;
+    uint32_t ff = fchunk * FW + fw;
     ff = ff < n_f ? ff : n_f - 1;
     w01s[i] = __ldg(w01g + (size_t)ff * XC_NTAP_PAD + tap);
     w2s[i] = __ldg(w2g + (size_t)ff * XC_NTAP_PAD + tap);
@@ -93,20 +96,20 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
 #pragma unroll
     for (int j = 0; j < XC_R; j++) pw[t][j] = 0.f;
 
-  const float4* w01w = w01s + warp * XC_NTAP_PAD;
-  const float2* w2w = w2s + warp * XC_NTAP_PAD;
+  const float4* w01w = w01s + fsub * XC_NTAP_PAD;
+  const float2* w2w = w2s + fsub * XC_NTAP_PAD;
 
   for (uint32_t m = 0; m < n_comb; m++) {
     const int smin = __ldg(smin_tab + m * n_fchunk + fchunk);
     const int off = __ldg(soff + m * n_f + fcl) - smin;
     __syncthreads();  // everyone is done with the previous tile (and, for m==0, the W stores are issued)
     for (uint32_t e = tid; e < tile_len; e += XC_THREADS) {
-      const size_t g = (size_t)i0 + smin + e;
+      const size_t g = (size_t)i0_blk + smin + e;
       tile[e] = g < n_cap ? load_iq<FMT>(iq, iq_base + g) : make_float2(0.f, 0.f);
     }
     __syncthreads();
 
-    const float2* xp = tile + off + lane * XC_R;
+    const float2* xp = tile + off + lsub * XC_TI + lane * XC_R;
     float2 acc[3][XC_R];
 #pragma unroll
     for (int t = 0; t < 3; t++)
@@ -157,14 +160,19 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
 int launch_xcorr_fold_fp32(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, const float4* d_w01,
                            const float2* d_w2, const int* d_soff, const int* d_smin, float* d_single_planar,
                            cudaStream_t st) {
-  const size_t smem = (size_t)XC_FW * XC_NTAP_PAD * (sizeof(float4) + sizeof(float2)) + (size_t)g.tile_len * sizeof(float2);
-  dim3 grid((LCS_N_FOLD + XC_TI - 1) / XC_TI, g.n_fchunk, batch), block(XC_THREADS);
-#define CALL(F)                                                                                                  \
-  cudaFuncSetAttribute(xcorr_fold_fp32_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-  xcorr_fold_fp32_kernel<F><<<grid, block, smem, st>>>(d_iq, d_w01, d_w2, d_soff, d_smin, d_single_planar, g.n_cap, \
-                                                       g.n_f, g.n_comb_xc, g.n_fchunk, g.tile_len)
+  const size_t smem = (size_t)g.fw * XC_NTAP_PAD * (sizeof(float4) + sizeof(float2)) + (size_t)g.tile_len * sizeof(float2);
+  const uint32_t ti_blk = XC_TI * (XC_FW / g.fw);
+  dim3 grid((LCS_N_FOLD + ti_blk - 1) / ti_blk, g.n_fchunk, batch), block(XC_THREADS);
+#define CALL_FW(F, W)                                                                                                \
+  cudaFuncSetAttribute(xcorr_fold_fp32_kernel<F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+  xcorr_fold_fp32_kernel<F, W><<<grid, block, smem, st>>>(d_iq, d_w01, d_w2, d_soff, d_smin, d_single_planar, g.n_cap, \
+                                                          g.n_f, g.n_comb_xc, g.n_fchunk, g.tile_len)
+#define CALL(F)                 \
+  if (g.fw == 1) { CALL_FW(F, 1); } \
+  else { CALL_FW(F, XC_FW); }
   LCS_DISPATCH_FMT(iq_format, CALL);
 #undef CALL
+#undef CALL_FW
   return 1;
 }
 
