@@ -190,6 +190,32 @@ lcs_status lcs_xcorr_peaks_batch_host(lcs_xcorr_plan* plan, const void* iq_host,
 lcs_status lcs_cell_search_batch_cu8(lcs_xcorr_plan* plan, const uint8_t* iq_host, uint32_t batch, lcs_cell* cells,
                                      uint32_t max_cells, uint32_t* n_cells);
 
+/* ---- streaming (tracker) mode: producer framing + one searcher cycle ------------------------------------------ */
+/* Host-side framing of a continuous raw IQ byte stream into searcher capture buffers: the searcher part of
+ * src/producer_thread.cpp:96-161.  A running time stamp (LTE samples modulo 19200) advances by
+ * (FS_LTE/16)/(fs_programmed*k_factor) per sample; after lcs_framer_request the capture of n_cap samples starts at the
+ * first sample whose stamp is within +-0.5 of 0 (mod 19200); `late` is that stamp wrapped to [-9600, 9600). */
+typedef struct lcs_framer lcs_framer;
+lcs_status lcs_framer_create(double fc_requested, double fc_programmed, double fs_programmed, uint32_t n_cap,
+                             lcs_framer** out);
+void lcs_framer_destroy(lcs_framer* framer);
+void lcs_framer_request(lcs_framer* framer);                /* capbuf_sync.request = true (searcher_thread.cpp:88) */
+double lcs_framer_sample_time(const lcs_framer* framer);    /* current time stamp (starts at -1) */
+/* Feed n_samples (I,Q) byte pairs received while the tracked frequency offset estimate is frequency_offset
+ * (global_thread_data.frequency_offset(); the reference re-reads it every 10000 samples).  *ready becomes 1 once a
+ * requested capture buffer is complete; *capbuf ([n_cap][2] bytes, owned by the framer, valid until the next request)
+ * and *late are then set. */
+lcs_status lcs_framer_push(lcs_framer* framer, const uint8_t* iq, uint32_t n_samples, double frequency_offset,
+                           int* ready, const uint8_t** capbuf, double* late);
+/* One cycle of the searcher thread (src/searcher_thread.cpp:95-232) on such a buffer: xcorr_pss at the single offset
+ * frequency_offset, threshold, peak_search, sss_detect, skip cells whose n_id_cell is in tracked_n_id_cell,
+ * pss_sss_foe / extract_tfg / tfoec / decode_mib.  For every NEW cell frame_timing = frame_start*(FS_LTE/16)/
+ * (fs_programmed*k_factor) + late, the value the reference hands to the cell's tracker (:214). */
+lcs_status lcs_tracker_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n_cap, double frequency_offset,
+                                  double fc_requested, double fc_programmed, double fs_programmed, double late,
+                                  const int32_t* tracked_n_id_cell, uint32_t n_tracked, lcs_cell* cells,
+                                  double* frame_timing, uint32_t max_cells, uint32_t* n_cells);
+
 #ifdef __cplusplus
 }
 #endif

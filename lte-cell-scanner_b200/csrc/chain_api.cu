@@ -44,7 +44,8 @@ static std::vector<cd> from_colmajor(const double* in, int n_rows, int n_cols) {
 // Per-peak stages of CellSearch.cpp:510-558 (sss_detect -> pss_sss_foe -> extract_tfg -> tfoec -> decode_mib) on a
 // device-resident capture buffer; cells that fail the SSS or MIB tests are dropped like in the reference.
 lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
-                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells) {
+                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells,
+                          const int32_t* tracked, uint32_t n_tracked) {
   const double THRESH2_N_SIGMA = 3;     // CellSearch.cpp:528
   lcs_status rc = LCS_OK;
   if (pk.empty()) {
@@ -60,6 +61,9 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
     if (rc != LCS_OK) return rc;
     if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
     c = o;
+    bool already_tracked = false;    // searcher_thread.cpp:153-174: cells that are being tracked are not examined further
+    for (uint32_t k = 0; k < n_tracked; k++) already_tracked |= tracked[k] == c.n_id_2 + 3 * c.n_id_1;
+    if (already_tracked) continue;
     rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
     if (rc != LCS_OK) return rc;
     c = o;
@@ -82,10 +86,10 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
   return LCS_OK;
 }
 
-// The chain of CellSearch.cpp:497-558 on a device-resident capture buffer.
-static lcs_status cell_search_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const double* f_search_set,
-                                  uint32_t n_f, double fc_req, double fc_prog, double fs_prog, lcs_cell* cells,
-                                  uint32_t max_cells, uint32_t* n_cells, lcs_cell* peaks, uint32_t* n_peaks) {
+// xcorr_pss + Z_th1 + peak_search (CellSearch.cpp:497-510) on a device-resident capture buffer; only the few values of
+// xc_incoherent_single that peak_search reads are fetched.
+static lcs_status peaks_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const double* f_search_set, uint32_t n_f,
+                            double fc_req, double fc_prog, double fs_prog, std::vector<lcs_cell>& pk) {
   const uint8_t DS_COMB_ARM = 2;        // CellSearch.cpp:484
   lcs_xcorr_plan* p = nullptr;
   lcs_status rc = get_cached_plan(ctx, n_cap, f_search_set, n_f, DS_COMB_ARM, fc_req, fc_prog, fs_prog, &p);
@@ -113,13 +117,23 @@ static lcs_status cell_search_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint
     if (e != cudaSuccess) fetch_err = e;
     return v;
   };
-  std::vector<lcs_cell> pk;
+  pk.clear();
   peak_search(pw.data(), fq.data(), z.data(), f_search_set, fc_req, fc_prog, single_at, DS_COMB_ARM, pk);
   LCS_CUDA(ctx, fetch_err);
+  return LCS_OK;
+}
+
+// The chain of CellSearch.cpp:497-558 on a device-resident capture buffer.
+static lcs_status cell_search_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const double* f_search_set,
+                                  uint32_t n_f, double fc_req, double fc_prog, double fs_prog, lcs_cell* cells,
+                                  uint32_t max_cells, uint32_t* n_cells, lcs_cell* peaks, uint32_t* n_peaks) {
+  std::vector<lcs_cell> pk;
+  lcs_status rc = peaks_dev(ctx, d_cap, fmt, n_cap, f_search_set, n_f, fc_req, fc_prog, fs_prog, pk);
+  if (rc != LCS_OK) return rc;
   if (n_peaks) *n_peaks = (uint32_t)pk.size();
   if (peaks)
     for (size_t i = 0; i < pk.size() && i < max_cells; i++) peaks[i] = pk[i];
-  return cell_chain_dev(ctx, d_cap, fmt, n_cap, pk, fc_req, fc_prog, fs_prog, cells, max_cells, n_cells);
+  return cell_chain_dev(ctx, d_cap, fmt, n_cap, pk, fc_req, fc_prog, fs_prog, cells, max_cells, n_cells, nullptr, 0);
 }
 
 }  // namespace lcs
@@ -261,6 +275,31 @@ lcs_status lcs_cell_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t
   LCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_cu8.p, capbuf_cu8, (size_t)n_cap * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
   return cell_search_dev(ctx, ctx->d_cu8.p, LCS_IQ_CU8, n_cap, f_search_set, n_f, fc_requested, fc_programmed,
                          fs_programmed, cells, max_cells, n_cells, peaks, n_peaks);
+}
+
+// One cycle of the tracker's searcher thread (src/searcher_thread.cpp:95-232) on a capture buffer delivered by the framer.
+lcs_status lcs_tracker_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n_cap, double frequency_offset,
+                                  double fc_requested, double fc_programmed, double fs_programmed, double late,
+                                  const int32_t* tracked_n_id_cell, uint32_t n_tracked, lcs_cell* cells, double* frame_timing,
+                                  uint32_t max_cells, uint32_t* n_cells) {
+  if (!ctx || !capbuf_cu8 || !n_cells || (n_tracked && !tracked_n_id_cell) || (max_cells && (!cells || !frame_timing)))
+    return fail(ctx, LCS_ERR_ARG, "tracker_search_cu8: null argument");
+  LCS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double f_search_set[1] = {frequency_offset};                                   // searcher_thread.cpp:96-98
+  const double k_factor = (fc_requested - frequency_offset) / fc_programmed;
+  LCS_CUDA(ctx, ctx->d_cu8.ensure((size_t)n_cap * 2));
+  LCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_cu8.p, capbuf_cu8, (size_t)n_cap * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
+  std::vector<lcs_cell> pk;
+  lcs_status rc = peaks_dev(ctx, ctx->d_cu8.p, LCS_IQ_CU8, n_cap, f_search_set, 1, fc_requested, fc_programmed, fs_programmed, pk);
+  if (rc != LCS_OK) return rc;
+  uint32_t found = 0;
+  rc = cell_chain_dev(ctx, ctx->d_cu8.p, LCS_IQ_CU8, n_cap, pk, fc_requested, fc_programmed, fs_programmed, cells, max_cells, &found,
+                      tracked_n_id_cell, n_tracked);
+  if (rc != LCS_OK) return rc;
+  for (uint32_t i = 0; i < found && i < max_cells; i++)                                  // searcher_thread.cpp:214
+    frame_timing[i] = cells[i].frame_start * (30720000.0 / 16) / (fs_programmed * k_factor) + late;
+  *n_cells = found;
+  return LCS_OK;
 }
 
 }  // extern "C"

@@ -95,7 +95,8 @@ lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_
                            double fc_req, double fc_prog, double fs_prog, lcs_xcorr_plan** out);
 void chain_scratch_release(lcs_ctx* ctx);   // chain_api.cu
 lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
-                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells);   // chain_api.cu
+                          double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells,
+                          const int32_t* tracked = nullptr, uint32_t n_tracked = 0);   // chain_api.cu
 // xcorr_tc.cu
 lcs_status tc_plan_setup(lcs_xcorr_plan* p);
 void tc_prof_dump();

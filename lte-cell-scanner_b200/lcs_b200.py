@@ -74,6 +74,12 @@ def lib():
         _lib.lcs_xcorr_plan_destroy.argtypes = [C.c_void_p]
         _lib.lcs_xcorr_plan_timing_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.lcs_xcorr_plan_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.lcs_framer_destroy.argtypes = [C.c_void_p]
+        _lib.lcs_framer_destroy.restype = None
+        _lib.lcs_framer_request.argtypes = [C.c_void_p]
+        _lib.lcs_framer_request.restype = None
+        _lib.lcs_framer_sample_time.argtypes = [C.c_void_p]
+        _lib.lcs_framer_sample_time.restype = C.c_double
     return _lib
 
 
@@ -250,6 +256,18 @@ class Context:
         return ([_copy(cells[i]) for i in range(min(n.value, max_cells))],
                 [_copy(peaks[i]) for i in range(min(npk.value, max_cells))])
 
+    def tracker_search_cu8(self, capbuf_cu8, frequency_offset, fc_requested, fc_programmed, fs_programmed, late,
+                           tracked=(), max_cells=16):
+        """One searcher-thread cycle (searcher_thread.cpp:95-232).  Returns [(Cell, frame_timing), ...] of NEW cells."""
+        cb = np.ascontiguousarray(capbuf_cu8, np.uint8)
+        tr = np.ascontiguousarray(list(tracked), np.int32)
+        cells = (Cell * max_cells)(); ft = (C.c_double * max_cells)(); n = C.c_uint32(0)
+        _chk(lib().lcs_tracker_search_cu8(self._h, _p(cb), C.c_uint32(cb.size // 2), C.c_double(frequency_offset),
+                                          C.c_double(fc_requested), C.c_double(fc_programmed), C.c_double(fs_programmed),
+                                          C.c_double(late), _p(tr) if tr.size else None, C.c_uint32(tr.size), cells, ft,
+                                          C.c_uint32(max_cells), C.byref(n)), self._h)
+        return [(_copy(cells[i]), ft[i]) for i in range(min(n.value, max_cells))]
+
     def plan(self, n_cap, f_set, ds_comb_arm, fc_requested, fc_programmed, fs_programmed, max_batch=1,
              kernel=KERNEL_AUTO):
         return XcorrPlan(self, n_cap, f_set, ds_comb_arm, fc_requested, fc_programmed, fs_programmed, max_batch, kernel)
@@ -340,6 +358,40 @@ class XcorrPlan:
         _chk(lib().lcs_cell_search_batch_cu8(self._h, C.c_void_p(host_ptr), C.c_uint32(batch), cells, C.c_uint32(max_cells), n),
              self.ctx._h)
         return [[_copy(cells[b * max_cells + k]) for k in range(min(n[b], max_cells))] for b in range(batch)]
+
+
+class Framer:
+    """lcs_framer: producer-side framing of a raw IQ byte stream into searcher capture buffers (host only)."""
+
+    def __init__(self, fc_requested, fc_programmed, fs_programmed, n_cap=153600):
+        self._h = C.c_void_p()
+        self.n_cap = n_cap
+        _chk(lib().lcs_framer_create(C.c_double(fc_requested), C.c_double(fc_programmed), C.c_double(fs_programmed),
+                                     C.c_uint32(n_cap), C.byref(self._h)))
+
+    def request(self):
+        lib().lcs_framer_request(self._h)
+
+    def sample_time(self):
+        return lib().lcs_framer_sample_time(self._h)
+
+    def push(self, iq_u8, frequency_offset):
+        """iq_u8: uint8 [n][2].  Returns None, or (capbuf uint8 [n_cap][2] copy, late) once a requested buffer is full."""
+        iq = np.ascontiguousarray(iq_u8, np.uint8)
+        ready = C.c_int(0); cap = C.POINTER(C.c_uint8)(); late = C.c_double(0)
+        _chk(lib().lcs_framer_push(self._h, _p(iq), C.c_uint32(iq.size // 2), C.c_double(frequency_offset), C.byref(ready),
+                                   C.byref(cap), C.byref(late)))
+        if not ready.value:
+            return None
+        return np.ctypeslib.as_array(cap, shape=(self.n_cap, 2)).copy(), late.value
+
+    def close(self):
+        if self._h:
+            lib().lcs_framer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def declared_symbols():

@@ -369,3 +369,37 @@ def test_cell_search_batch_matches_single(ctx, lcs, capbuf0000):
         for a, b in zip(cells, ref_cells):
             assert a.as_dict() == b.as_dict()
     plan.close()
+
+
+def test_tracker_search_cycle(ctx, lcs, capbuf0000):
+    """Streaming mode: raw bytes -> lcs_framer -> lcs_tracker_search_cu8 == the n_f=1 chain of
+    searcher_thread.cpp:95-232 on the framed buffer; frame_timing = frame_start*(FS_LTE/16)/(fs*k)+late; tracked cells
+    are skipped."""
+    fc = capbuf0000["fc"]
+    real = capbuf0000["cu8"]
+    full, _ = ctx.cell_search(real, lcs.f_search_set(fc, 120.0), fc, fc, 1.92e6)
+    f_off = float(np.round(full[0].freq_superfine))          # the tracker searches at its current offset estimate
+    fs = 1.92e6
+    rng = np.random.default_rng(5)
+    lead = rng.integers(100, 156, size=(19200 + 777, 2), dtype=np.uint8)
+    stream = np.concatenate([lead, real, lead])
+    fr = lcs.Framer(fc, fc, fs, real.shape[0])
+    fr.push(stream[:500], f_off)
+    fr.request()
+    got = None
+    for lo in range(500, stream.shape[0], 10000):            # BLOCK_SIZE of producer_thread.cpp:95
+        got = got or fr.push(stream[lo:lo + 10000], f_off)
+    assert got is not None
+    cap, late = got
+    assert abs(late) < 0.5
+    k = (fc - f_off) / fc
+    ref_cells, _ = ctx.cell_search(cap, np.array([f_off]), fc, fc, fs)
+    new = ctx.tracker_search_cu8(cap, f_off, fc, fc, fs, late)
+    assert len(new) == len(ref_cells) >= 1
+    for (c, ft), r in zip(new, ref_cells):
+        assert c.as_dict() == r.as_dict()
+        assert ft == r.frame_start * (30720000.0 / 16) / (fs * k) + late
+    first = new[0][0].n_id_cell()
+    rest = ctx.tracker_search_cu8(cap, f_off, fc, fc, fs, late, tracked=[first])
+    assert [c.n_id_cell() for c, _ in rest] == [c.n_id_cell() for c, _ in new if c.n_id_cell() != first]
+    fr.close()

@@ -118,3 +118,57 @@ def test_dedup_matches_oracle(lcs, oracle):
     assert [(c.n_id_cell(), c.fc_requested, c.pss_pow) for c in a] == [(c.n_id_cell(), c.fc_requested, c.pss_pow) for c in b]
     assert [(c.n_id_cell(), c.fc_requested) for c in a] == [(277, 739.1e6), (271, 739e6), (277, 741e6)]
     assert lcs.dedup([]) == []
+
+
+def _producer_restatement(stream, fc_req, fc_prog, fs_prog, f_off, n_cap, request_at):
+    """src/producer_thread.cpp:96-161 written out directly (searcher capture buffer only): returns (start index, late)."""
+    import math
+    k = (fc_req - f_off) / fc_prog
+    st = -1.0
+    request = False
+    for t in range(stream.shape[0]):
+        if t == request_at:
+            request = True
+        st += (30720000.0 / 16) / (fs_prog * k)
+        if st > 19200.0:
+            st -= 19200.0
+        w = (st + 9600.0) - 19200.0 * math.floor((st + 9600.0) / 19200.0) - 9600.0
+        if request and abs(w) < 0.5:
+            return t, w
+    return None, None
+
+
+def test_framer_matches_producer_thread(lcs):
+    """lcs_framer (host framing of a raw IQ stream) against a direct restatement of producer_thread.cpp:96-161: capture
+    starts at the first sample whose time stamp is within +-0.5 of a frame-pair boundary after the request, `late` is that
+    stamp, the buffer holds the next n_cap samples verbatim; pushes of ragged block sizes give the same answer."""
+    L = lcs
+    rng = np.random.default_rng(11)
+    n_cap = 5000
+    stream = rng.integers(0, 256, size=(60000, 2), dtype=np.uint8)
+    for fc_req, fc_prog, fs_prog, f_off, req_at in [(739e6, 739e6, 1.92e6, 0.0, 0), (739e6, 739.002e6, 1.92e6 * 1.00003, 1234.5, 7000),
+                                                   (2.1e9, 2.1e9, 1.92e6 * 0.99995, -30000.0, 19190)]:
+        t0, late = _producer_restatement(stream, fc_req, fc_prog, fs_prog, f_off, n_cap, req_at)
+        assert t0 is not None
+        for blocks in ([10000] * 6, [1, 6999, 3, 12187, 810, 40000]):
+            fr = L.Framer(fc_req, fc_prog, fs_prog, n_cap)
+            pos, got = 0, None
+            requested = False
+            for b in blocks:
+                # the request arrives between two samples: split the block there
+                parts = [(pos, pos + b)]
+                if not requested and pos <= req_at < pos + b:
+                    parts = [(pos, req_at), (req_at, pos + b)]
+                for lo, hi in parts:
+                    if lo == req_at and not requested:
+                        fr.request(); requested = True
+                    if hi > lo:
+                        r = fr.push(stream[lo:hi], f_off)
+                        if r is not None and got is None:
+                            got = r
+                pos += b
+            assert got is not None
+            cap, glate = got
+            assert glate == late
+            assert np.array_equal(cap, stream[t0:t0 + n_cap])
+            fr.close()
