@@ -1,6 +1,9 @@
 // lcs_api.cu - context, xcorr plan and the xcorr_pss entry points of the C ABI (include/lcs_b200.h).
 #include <cmath>
 #include <cstdio>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -407,12 +410,18 @@ lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_
     }
   }
   lcs_xcorr_plan* p = nullptr;
+  static const bool trace = std::getenv("LCS_TRACE_PLANS") != nullptr;     // debug aid: host cost of plan turnover
+  const auto t0 = std::chrono::steady_clock::now();
   lcs_status rc = build_plan(ctx, n_cap, f_search_set, n_f, arm, fc_req, fc_prog, fs_prog, 1, LCS_KERNEL_AUTO, &p);
   if (rc != LCS_OK) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   if (ctx->cached_plans.size() >= 8) {
     delete ctx->cached_plans.front();
     ctx->cached_plans.erase(ctx->cached_plans.begin());
   }
+  if (trace)
+    std::fprintf(stderr, "[lcs] plan build %.3f ms, evict %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   ctx->cached_plans.push_back(p);
   *out = p;
   return LCS_OK;

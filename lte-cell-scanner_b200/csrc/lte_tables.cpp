@@ -24,7 +24,7 @@ void pss_fd(int n_id_2, cd out[62]) {
 // 128-point time-domain PSS with a 9-sample cyclic prefix (137 taps), scaled so that
 // sigpower(td)==sigpower of the 62 occupied bins spread over 128.  Reference: src/lte_lib.cpp:177-188
 // (idft(...)*sqrt(128/62), idft = ifft*sqrt(N)).  Direct O(N^2) inverse DFT in double.
-void pss_td(int n_id_2, cd out[137]) {
+static void pss_td_compute(int n_id_2, cd out[137]) {
   cd fd[62], X[128];
   pss_fd(n_id_2, fd);
   for (int i = 0; i < 128; i++) X[i] = 0;
@@ -46,6 +46,12 @@ void pss_td(int n_id_2, cd out[137]) {
   }
   for (int i = 0; i < 9; i++) out[i] = td[119 + i];
   for (int i = 0; i < 128; i++) out[9 + i] = td[i];
+}
+// The three sequences are constants: computed once (a plan is built per centre frequency of a sweep).
+void pss_td(int n_id_2, cd out[137]) {
+  struct Tab { cd v[3][137]; Tab() { for (int t = 0; t < 3; t++) pss_td_compute(t, v[t]); } };
+  static const Tab tab;
+  for (int i = 0; i < 137; i++) out[i] = tab.v[n_id_2][i];
 }
 
 // SSS in the frequency domain as +-1 integers.  Reference: src/lte_lib.cpp:199-257 (3GPP 36.211 6.11.2).
