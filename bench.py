@@ -78,17 +78,52 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): one
-    `nvidia-smi -lms 20` process runs across the region; only samples stamped inside it are kept."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  A thread polls NVML every 5 ms
+    (pynvml; the GIL is released while the main thread waits on CUDA); if NVML is unavailable one `nvidia-smi -lms 20`
+    process runs across the region instead.  Only samples stamped inside the region are kept."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                    0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.t0 = self.t1 = None
+        self.nvml_rows = []
+        self.thread = None
+        self.stop = False
+
+    def _nvml_loop(self, h, nv):
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                self.nvml_rows.append((time.time(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -104,6 +139,19 @@ class ClockSampler:
         self.t1 = time.time()
 
     def summary(self):
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=1)
+            inside = [r for r in self.nvml_rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+            use = inside if inside else self.nvml_rows
+            reasons = set()
+            for r in use:
+                for bit, name in self.NVML_REASONS.items():
+                    if r[3] & bit:
+                        reasons.add(name)
+            return dict(sm_mhz=float(np.median([r[1] for r in use])) if use else None, sm_max_mhz=float(self.sm_max),
+                        power_w_max=max([r[2] for r in use]) if use else None, reasons=sorted(reasons), samples=len(inside),
+                        samples_total=len(self.nvml_rows), source="nvml, 5 ms period")
         rows = []
         if self.proc is not None:
             time.sleep(0.05)
@@ -227,9 +275,9 @@ def cpu_baseline_leg(f, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=192, help="capture buffers per rank per step")
+    ap.add_argument("--batch", type=int, default=384, help="capture buffers per rank per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

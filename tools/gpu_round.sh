@@ -8,6 +8,7 @@ python tools/gpu_margins.py > gpurun_out/margins_$TAG.log 2>&1; cat gpurun_out/m
 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
 python bench.py --steps 10 --warmup 3 --kernel fp32 --no-cpu-baseline > gpurun_out/bench_fp32_$TAG.json 2>> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_fp32_$TAG.json
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>&1; cat gpurun_out/bench_ref_$TAG.json
+python bench.py --workload tracker --batch 256 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tracker_$TAG.json 2>> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_tracker_$TAG.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_bench_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:xcorr_fold_tc -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
