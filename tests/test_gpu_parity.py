@@ -277,12 +277,16 @@ def test_tc_synthetic_batch_and_extremes(ctx, lcs, oracle):
 
 
 def test_tc_edge_shapes(ctx, lcs, oracle):
-    """n_f=1, n_f=42 (one full 126-row chunk), 51 (two chunks), short buffer, fc_programmed != fc_requested, arm=0/1."""
+    """Chunking of the template columns (<= 32 hypotheses = 96 columns per launch): n_f=1 (32-column kernel), 42 (2 x 21 ->
+    64-column kernel), 51 (26+25 -> 96-column kernel), 64 (2 full chunks), 70 (3 chunks); short buffers,
+    fc_programmed != fc_requested, arm=0/1."""
     cases = [
         (153600, np.array([35000.0]), 2, 739e6, 739e6, 1.92e6),
         (40000, np.arange(-20, 22) * 2500.0, 2, 739e6, 739.002e6, 1.92e6 * 1.00001),
         (29000, np.array([-20000.0, 0.0, 5000.0]), 0, 2.1e9, 2.1e9, 1.92e6),
         (30000, np.arange(-25, 26) * 3000.0, 1, 739e6, 739e6, 1.92e6),          # 51 hypotheses -> 2 chunks
+        (30000, np.arange(-32, 32) * 2000.0 + 500.0, 2, 739e6, 739e6, 1.92e6),  # 64 hypotheses -> 2 x 32 (all 96 columns live)
+        (30000, np.arange(-35, 35) * 1500.0, 2, 1.8e9, 1.8e9, 1.92e6),          # 70 hypotheses -> 3 chunks
     ]
     for i, (n_cap, f, arm, fcr, fcp, fs) in enumerate(cases):
         _tc_vs_oracle(ctx, lcs, oracle, synth_cu8(77 + i, n_cap)[None], f, fcr, fcp, fs, arm)
