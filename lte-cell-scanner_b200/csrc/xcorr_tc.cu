@@ -26,10 +26,12 @@
 // shared-memory descriptor with LBO = SBO = 128 B addresses the whole Hankel tile.  The template digit planes
 // stay resident in shared memory in core-matrix order (LBO 128 B, SBO 2304 B).
 //
-// Per CTA (persistent, one per SM): warp 0 builds P tiles, warp 1 issues the MMAs (one elected lane, 9 UTCIMMA per
-// (sub-tile, re/im, digit) plane into a ring of 4 TMEM accumulator planes), warps 2-17 read the planes back
-// (tcgen05.ld), recombine the digits, turn them into |xc|^2 and fold the 15 half frames into per-template
-// accumulators in shared memory.  Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
+// Per CTA (persistent, one per SM): warp 0 builds P tiles, warp 1 issues the MMAs (one elected lane; per sub-tile and
+// re/im part a "wide" job - digit planes 0|1 side by side, N = 2*npad, 9 UTCIMMA - into one of two 192-column TMEM slots
+// and a "narrow" job - digit plane 2, N = npad - into a third slot), the epilogue warps (4 per group of NC template
+// columns, one per TMEM lane quarter) read the slots back (tcgen05.ld), recombine the digits, turn them into |xc|^2 and
+// fold the 15 half frames into per-template accumulators in shared memory.
+// Output: xc_incoherent_single, planar [batch][3][n_f][9600] float.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -138,46 +140,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          (1ull << 46);
 }
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand from TMEM (M rows on the 128 lanes, K bytes packed along the columns), B from shared memory.
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
 // Variants guarded by an "elected lane" flag so that the issuing warp stays convergent: the compiler then keeps
 // descriptors in uniform registers and emits one UTCIMMA per call instead of an elect-and-loop sequence.
 __device__ __forceinline__ uint32_t elect_one_flag() {
   uint32_t r;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(r));
   return r;
-}
-__device__ __forceinline__ void umma_i8_ts_g(uint32_t flag, uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "setp.ne.b32 q, %5, 0;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate), "r"(flag)
-      : "memory");
 }
 __device__ __forceinline__ void umma_i8_g(uint32_t flag, uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -192,24 +160,11 @@ __device__ __forceinline__ void umma_i8_g(uint32_t flag, uint32_t d_tmem, uint64
 __device__ __forceinline__ void umma_commit_g(uint32_t flag, uint32_t bar) {
   asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar), "r"(flag) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
