@@ -301,7 +301,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("LCS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at every NCCL_DEBUG level
+        # (VERSION, WARN, INFO); drop the variable unless asked for, and send any NCCL log to stderr
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("LCS_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["LCS_NCCL_DEBUG"]
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     f = f_grid() if args.workload == "search" else np.array([0.0])      # searcher_thread.cpp:97-98: one offset
