@@ -172,3 +172,49 @@ def test_framer_matches_producer_thread(lcs):
             assert glate == late
             assert np.array_equal(cap, stream[t0:t0 + n_cap])
             fr.close()
+
+
+def test_tc_integer_formulation_numpy(oracle):
+    """The arithmetic of the tcgen05 correlator restated in numpy integers and checked against the oracle's
+    `xc`: 24-bit fixed-point templates in three balanced base-256 digits, x' = byte-128, second byte stream (Q', ~I') for the
+    imaginary part, additive corrections sum(a) / sum(a[even]), int32-safe partial sums, exact reconstruction."""
+    from conftest import synth_cu8, cu8_to_c128
+    n_cap, fc, fs = 12000, 739e6, 1.92e6
+    f = np.array([-40000.0, 5000.0, 70000.0])
+    cu8 = synth_cu8(99, n_cap, sigma=40.0)
+    cu8[100:130] = 255; cu8[500:520] = 0                       # saturated samples: the "+1" correction must hold there too
+    ref = oracle.xcorr_pss(cu8_to_c128(cu8), f, 2, fc, fc, fs, want_xc=True, want_sp=False)["xc"]     # [3][n_cap-136][n_f]
+    z = cu8.reshape(-1).astype(np.int64)                       # interleaved I,Q bytes
+    xs = z - 128                                               # (I', Q')
+    ys = np.empty_like(xs); ys[0::2] = xs[1::2]; ys[1::2] = -xs[0::2] - 1      # (Q', ~I')
+    w = np.empty((f.size, 3, 137), np.complex128)
+    for fi, fo in enumerate(f):
+        k_factor = (fc - fo) / fc
+        k = np.pi * fo / ((fs * k_factor) / 2)
+        for t in range(3):
+            w[fi, t] = np.conj(oracle.pss_td(t) * np.exp(1j * k * np.arange(137))) / 137
+    maxabs = max(np.abs(w.real).max(), np.abs(w.imag).max())
+    limit = 127 * 65536 + 127 * 256 + 127
+    e = int(np.floor(np.log2(limit / maxabs)))
+    S = 2.0 ** e
+    assert maxabs * S <= limit
+    lags = np.random.default_rng(1).integers(0, n_cap - 136, 150)
+    worst = 0.0
+    for fi in range(f.size):
+        for t in range(3):
+            wr, wi = np.rint(w[fi, t].real * S).astype(np.int64), np.rint(w[fi, t].imag * S).astype(np.int64)
+            a = np.empty(274, np.int64); a[0::2] = wr; a[1::2] = -wi
+            d2 = ((a + 128) % 256) - 128; r1 = (a - d2) // 256
+            d1 = ((r1 + 128) % 256) - 128; d0 = (r1 - d1) // 256
+            assert np.array_equal((d0 * 256 + d1) * 256 + d2, a)
+            assert d0.min() >= -128 and d0.max() <= 127 and d1.min() >= -128 and d2.max() <= 127
+            c_re, c_im = a.sum(), a[0::2].sum()
+            for L in lags:
+                seg_x, seg_y = xs[2 * L:2 * L + 274], ys[2 * L:2 * L + 274]
+                acc = [[int((d * s).sum()) for d in (d0, d1, d2)] for s in (seg_x, seg_y)]
+                assert max(abs(v) for part in acc for v in part) < 2 ** 23          # fits the int32 accumulators with room
+                v_re = (acc[0][0] * 256 + acc[0][1]) * 256 + acc[0][2] + c_re
+                v_im = (acc[1][0] * 256 + acc[1][1]) * 256 + acc[1][2] + c_im
+                got = complex(v_re, v_im) / (S * 128)
+                worst = max(worst, abs(got - ref[t, L, fi]) / np.abs(ref[t, :, fi]).max())
+    assert worst < 3e-7, worst            # float32 rounding of the reference's stored xc + 2^-24 template quantisation
