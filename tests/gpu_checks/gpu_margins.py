@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(ROOT, "lte-cell-scanner_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import lcs_b200 as L

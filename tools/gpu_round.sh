@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu_$TAG.log
-python tools/gpu_margins.py > gpurun_out/margins_$TAG.log 2>&1; cat gpurun_out/margins_$TAG.log
+python tests/gpu_checks/gpu_margins.py > gpurun_out/margins_$TAG.log 2>&1; cat gpurun_out/margins_$TAG.log
 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
 python bench.py --steps 10 --warmup 3 --kernel fp32 --no-cpu-baseline > gpurun_out/bench_fp32_$TAG.json 2>> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_fp32_$TAG.json
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>&1; cat gpurun_out/bench_ref_$TAG.json
