@@ -25,6 +25,22 @@ struct DevBuf {   // owning device allocation
   cudaError_t ensure(size_t count) { return (p && n >= count) ? cudaSuccess : alloc(count); }
 };
 
+template <class T>
+struct PinBuf {   // owning page-locked host allocation (asynchronous device-to-host copies need one)
+  T* p = nullptr;
+  size_t n = 0;
+  PinBuf() {}
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t count) {
+    if (p && n >= count) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; }
+    n = count;
+    return cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+};
+
 }  // namespace lcs
 
 struct lcs_xcorr_plan;
@@ -78,6 +94,8 @@ struct lcs_xcorr_plan {
     lcs::DevBuf<double> work;
     lcs::DevBuf<unsigned char> peaks;
     lcs::DevBuf<int32_t> npeaks;
+    lcs::PinBuf<unsigned char> h_peaks;   // page-locked landing zones of the peak lists
+    lcs::PinBuf<int32_t> h_npeaks;
   } hb[2];
 };
 

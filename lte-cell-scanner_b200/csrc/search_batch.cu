@@ -155,10 +155,13 @@ static lcs_status search_batch(lcs_xcorr_plan* p, const void* h_iq, int iq_forma
     LCS_CUDA(ctx, hb.work.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.peaks.ensure((size_t)chunk * SEARCH_MAX_PEAKS * sizeof(DevPeak)));
     LCS_CUDA(ctx, hb.npeaks.ensure(chunk));
+    // page-locked: with pageable memory cudaMemcpyAsync would block the host until the chunk's kernels are done and the
+    // next chunk could not be queued behind it
+    LCS_CUDA(ctx, hb.h_peaks.ensure((size_t)chunk * SEARCH_MAX_PEAKS * sizeof(DevPeak)));
+    LCS_CUDA(ctx, hb.h_npeaks.ensure(chunk));
   }
-  std::vector<DevPeak> h_peaks[2];
-  std::vector<int32_t> h_np[2];
-  for (int s = 0; s < 2; s++) { h_peaks[s].resize((size_t)chunk * SEARCH_MAX_PEAKS); h_np[s].resize(chunk); }
+  const DevPeak* h_peaks[2] = {reinterpret_cast<const DevPeak*>(p->hb[0].h_peaks.p), reinterpret_cast<const DevPeak*>(p->hb[1].h_peaks.p)};
+  const int32_t* h_np[2] = {p->hb[0].h_npeaks.p, p->hb[1].h_npeaks.p};
   auto issue = [&](uint32_t b0, int s) -> lcs_status {
     const uint32_t nb = std::min(chunk, batch - b0);
     cudaStream_t st = ctx->streams[s];
@@ -173,8 +176,8 @@ static lcs_status search_batch(lcs_xcorr_plan* p, const void* h_iq, int iq_forma
     rc = launch_peak_search(p, nb, hb.pow.p, hb.frq.p, hb.spi.p, hb.single.p, hb.work.p, reinterpret_cast<DevPeak*>(hb.peaks.p),
                             hb.npeaks.p, SEARCH_MAX_PEAKS, st);
     if (rc != LCS_OK) return rc;
-    LCS_CUDA(ctx, cudaMemcpyAsync(h_np[s].data(), hb.npeaks.p, nb * 4, cudaMemcpyDeviceToHost, st));
-    LCS_CUDA(ctx, cudaMemcpyAsync(h_peaks[s].data(), hb.peaks.p, (size_t)nb * SEARCH_MAX_PEAKS * sizeof(DevPeak), cudaMemcpyDeviceToHost, st));
+    LCS_CUDA(ctx, cudaMemcpyAsync(hb.h_npeaks.p, hb.npeaks.p, nb * 4, cudaMemcpyDeviceToHost, st));
+    LCS_CUDA(ctx, cudaMemcpyAsync(hb.h_peaks.p, hb.peaks.p, (size_t)nb * SEARCH_MAX_PEAKS * sizeof(DevPeak), cudaMemcpyDeviceToHost, st));
     return LCS_OK;
   };
   auto finish = [&](uint32_t b0, int s) -> lcs_status {
