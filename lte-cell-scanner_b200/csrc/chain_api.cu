@@ -1,24 +1,19 @@
 // chain_api.cu - C-ABI entry points for the stages after xcorr_pss (include/lcs_b200.h).
 #include <cmath>
 #include <cstring>
-#include <map>
-#include <mutex>
 
 #include "chain_gpu.hpp"
 
 namespace lcs {
 
-static std::mutex g_cs_mu;
-static std::map<lcs_ctx*, std::unique_ptr<ChainScratch>> g_cs;
+// per-context scratch of the companion kernels, owned by the context (one thread per context, see lcs_b200.h)
 ChainScratch& chain_scratch(lcs_ctx* ctx) {
-  std::lock_guard<std::mutex> lk(g_cs_mu);
-  auto& p = g_cs[ctx];
-  if (!p) p.reset(new ChainScratch());
-  return *p;
+  if (!ctx->chain) ctx->chain = new ChainScratch();
+  return *static_cast<ChainScratch*>(ctx->chain);
 }
 void chain_scratch_release(lcs_ctx* ctx) {
-  std::lock_guard<std::mutex> lk(g_cs_mu);
-  g_cs.erase(ctx);
+  delete static_cast<ChainScratch*>(ctx->chain);
+  ctx->chain = nullptr;
 }
 
 static lcs_status upload_c128(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap) {
@@ -45,7 +40,7 @@ static std::vector<cd> from_colmajor(const double* in, int n_rows, int n_cols) {
 // device-resident capture buffer; cells that fail the SSS or MIB tests are dropped like in the reference.
 lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
                           double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells,
-                          const int32_t* tracked, uint32_t n_tracked) {
+                          const int32_t* tracked, uint32_t n_tracked, bool tracker_cycle) {
   const double THRESH2_N_SIGMA = 3;     // CellSearch.cpp:528
   lcs_status rc = LCS_OK;
   if (pk.empty()) {
@@ -54,6 +49,8 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
   }
   ChainScratch& cs = chain_scratch(ctx);
   uint32_t found = 0;
+  const bool tracked_mode = tracker_cycle;
+  std::vector<int> accepted_ids;
   for (lcs_cell c : pk) {
     lcs_cell o;
     rc = dev_sss_detect(ctx, cs, d_cap, fmt, n_cap, c, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, o, nullptr);
@@ -61,8 +58,12 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
     if (rc != LCS_OK) return rc;
     if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
     c = o;
-    bool already_tracked = false;    // searcher_thread.cpp:153-174: cells that are being tracked are not examined further
+    // searcher_thread.cpp:153-174: cells that are being tracked are not examined further.  The reference appends every new
+    // cell to tracked_cell_list inside this loop (:216-219), so a later peak of the same buffer with the same id is skipped too.
+    bool already_tracked = false;
     for (uint32_t k = 0; k < n_tracked; k++) already_tracked |= tracked[k] == c.n_id_2 + 3 * c.n_id_1;
+    if (tracked_mode)
+      for (int id : accepted_ids) already_tracked |= id == c.n_id_2 + 3 * c.n_id_1;
     if (already_tracked) continue;
     rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
     if (rc != LCS_OK) return rc;
@@ -81,6 +82,7 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
     if (o.n_rb_dl == -1) continue;  // CellSearch.cpp:554-558
     if (found < max_cells && cells) cells[found] = o;
     found++;
+    accepted_ids.push_back(o.n_id_2 + 3 * o.n_id_1);
   }
   if (n_cells) *n_cells = found;
   return LCS_OK;
@@ -100,7 +102,8 @@ static lcs_status peaks_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n
   LCS_CUDA(ctx, ctx->d_pow.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_frq.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_spi.ensure(LCS_N_FOLD));
-  rc = lcs_xcorr_pss_device(p, d_cap, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p, nullptr, st);
+  LCS_CUDA(ctx, ctx->d_spp.ensure((size_t)p->ps.geom.n_comb_sp * LCS_N_FOLD));
+  rc = plan_run_device(p, d_cap, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p, nullptr, ctx->d_spp.p, st);
   if (rc != LCS_OK) return rc;
   std::vector<double> pw(3 * LCS_N_FOLD), spi(LCS_N_FOLD), z(LCS_N_FOLD);
   std::vector<int32_t> fq(3 * LCS_N_FOLD);
@@ -108,7 +111,7 @@ static lcs_status peaks_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n
   LCS_CUDA(ctx, cudaMemcpyAsync(fq.data(), ctx->d_frq.p, fq.size() * 4, cudaMemcpyDeviceToHost, st));
   LCS_CUDA(ctx, cudaMemcpyAsync(spi.data(), ctx->d_spi.p, spi.size() * 8, cudaMemcpyDeviceToHost, st));
   LCS_CUDA(ctx, cudaStreamSynchronize(st));
-  calc_z_th1(spi.data(), LCS_N_FOLD, (uint16_t)p->geom.n_comb_xc, DS_COMB_ARM, z.data());
+  calc_z_th1(spi.data(), LCS_N_FOLD, (uint16_t)p->ps.geom.n_comb_xc, DS_COMB_ARM, z.data());
   // peak_search reads xc_incoherent_single only at (2*arm+1) positions per peak: fetch those on demand.
   cudaError_t fetch_err = cudaSuccess;
   auto single_at = [&](int t, int f, int idx) -> float {
@@ -294,7 +297,7 @@ lcs_status lcs_tracker_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint3
   if (rc != LCS_OK) return rc;
   uint32_t found = 0;
   rc = cell_chain_dev(ctx, ctx->d_cu8.p, LCS_IQ_CU8, n_cap, pk, fc_requested, fc_programmed, fs_programmed, cells, max_cells, &found,
-                      tracked_n_id_cell, n_tracked);
+                      tracked_n_id_cell, n_tracked, true);
   if (rc != LCS_OK) return rc;
   for (uint32_t i = 0; i < found && i < max_cells; i++)                                  // searcher_thread.cpp:214
     frame_timing[i] = cells[i].frame_start * (30720000.0 / 16) / (fs_programmed * k_factor) + late;

@@ -366,7 +366,7 @@ lcs_status dev_pss_sss_foe(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, in
   if (first - 9600 * k_factor > -0.5) { first -= 9600 * k_factor; sn = 10; } else sn = 0;
   const std::vector<double> locs = mrange(first, 9600 * fs_ratio * k_factor, (double)((long)n_cap - 127 - dist - 100));
   const int n_sss = (int)locs.size();
-  if (n_sss < 1) { out = cell; out.freq_fine = NAN; return LCS_OK; }
+  if (n_sss < 1) { out = cell; out.freq_fine = cell.freq; return LCS_OK; }   // reference: M stays 0, arg(0) = 0 (searcher.cpp:806,848)
   std::vector<int> starts;
   for (int k = 0; k < n_sss; k++) {
     const long s = (long)std::rint(locs[k]);

@@ -24,144 +24,73 @@ lcs_status fail(lcs_ctx* ctx, lcs_status st, const std::string& msg) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Plan construction: templates, fold offsets, geometry.
+// Plan construction: one search configuration wrapped around a plan set (planset.cu).
 // ---------------------------------------------------------------------------------------------
 static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_set, uint32_t n_f, uint8_t arm,
                              double fc_req, double fc_prog, double fs_prog, uint32_t max_batch, int kernel,
                              lcs_xcorr_plan** out) {
   if (!ctx || !f_search_set || !out) return fail(ctx, LCS_ERR_ARG, "xcorr plan: null argument");
   if (n_f == 0 || n_f > 4096) return fail(ctx, LCS_ERR_ARG, "xcorr plan: n_f out of range");
-  if (n_cap < 136 + 100 + LCS_N_FOLD || n_cap < 273 + LCS_N_FOLD)
-    return fail(ctx, LCS_ERR_ARG, "xcorr plan: capture buffer shorter than one 5 ms half frame + margins");
-  if (arm > 64) return fail(ctx, LCS_ERR_ARG, "xcorr plan: ds_comb_arm out of range");
   if (max_batch == 0) max_batch = 1;
-  LCS_CUDA(ctx, cudaSetDevice(ctx->device));
-
   std::unique_ptr<lcs_xcorr_plan> p(new lcs_xcorr_plan());
   p->ctx = ctx;
-  p->f_search_set.assign(f_search_set, f_search_set + n_f);
-  p->fc_requested = fc_req;
-  p->fc_programmed = fc_prog;
-  p->fs_programmed = fs_prog;
   p->max_batch = max_batch;
   p->kernel = kernel;
-  XcorrGeom& g = p->geom;
-  g.n_cap = n_cap;
-  g.n_f = n_f;
-  g.ds_comb_arm = arm;
-  const uint32_t n_lag = n_cap - 136;
-  g.n_comb_xc = (n_lag - 100) / LCS_N_FOLD;      // searcher.cpp:276
-  g.n_comb_sp = (n_cap - 136 - 137) / LCS_N_FOLD;  // searcher.cpp:194
-  g.fw = n_f == 1 ? 1 : XC_FW;                    // searcher_thread.cpp:97-98 searches a single offset
-  g.n_fchunk = (n_f + g.fw - 1) / g.fw;
-
-  // Templates: conj(fshift(pss_td[t], f_off, fs_programmed*k_factor))/137  (searcher.cpp:145-151),
-  // computed in double exactly like dsp.h:40-53 (cos/sin of k*t) and rounded once to fp32.
-  cd td[3][137];
-  for (int t = 0; t < 3; t++) pss_td(t, td[t]);
-  const double kPi = 3.14159265358979323846;
-  p->h_w.assign((size_t)n_f * 3 * 137, cd(0, 0));
-  std::vector<float4> w01((size_t)n_f * XC_NTAP_PAD, make_float4(0, 0, 0, 0));
-  std::vector<float2> w2((size_t)n_f * XC_NTAP_PAD, make_float2(0, 0));
-  std::vector<int> soff((size_t)g.n_comb_xc * n_f);
-  for (uint32_t f = 0; f < n_f; f++) {
-    const double f_off = f_search_set[f];
-    const double k_factor = (fc_req - f_off) / fc_prog;  // :147
-    const double k = kPi * f_off / ((fs_prog * k_factor) / 2);
-    for (int tap = 0; tap < 137; tap++) {
-      const cd rot(std::cos(k * tap), std::sin(k * tap));
-      cd w[3];
-      for (int t = 0; t < 3; t++) {
-        w[t] = std::conj(td[t][tap] * rot) / 137.0;
-        p->h_w[((size_t)f * 3 + t) * 137 + tap] = w[t];
-      }
-      w01[(size_t)f * XC_NTAP_PAD + tap] = make_float4((float)w[0].real(), (float)w[0].imag(), (float)w[1].real(), (float)w[1].imag());
-      w2[(size_t)f * XC_NTAP_PAD + tap] = make_float2((float)w[2].real(), (float)w[2].imag());
-    }
-    for (uint32_t m = 0; m < g.n_comb_xc; m++) {
-      const double s = std::rint(m * .005 * k_factor * fs_prog);  // :298 (IT++ round_i == rint)
-      if (s < 0 || s + (LCS_N_FOLD - 1) >= (double)n_lag)
-        return fail(ctx, LCS_ERR_RANGE, "xcorr plan: fold offset runs past the correlation buffer (reference would read out of bounds)");
-      soff[(size_t)m * n_f + f] = (int)s;
-    }
-  }
-  p->h_soff = soff;
-  std::vector<int> smin((size_t)g.n_comb_xc * g.n_fchunk);
-  uint32_t max_spread = 0;
-  for (uint32_t m = 0; m < g.n_comb_xc; m++)
-    for (uint32_t c = 0; c < g.n_fchunk; c++) {
-      int lo = INT32_MAX, hi = INT32_MIN;
-      for (uint32_t f = c * g.fw; f < std::min(n_f, (c + 1) * g.fw); f++) {
-        lo = std::min(lo, soff[(size_t)m * n_f + f]);
-        hi = std::max(hi, soff[(size_t)m * n_f + f]);
-      }
-      smin[(size_t)m * g.n_fchunk + c] = lo;
-      max_spread = std::max(max_spread, (uint32_t)(hi - lo));
-    }
-  g.max_spread = max_spread;
-  g.tile_len = XC_TI * (XC_FW / g.fw) + XC_NTAP_PAD + max_spread + 8;
-  const size_t smem = (size_t)g.fw * XC_NTAP_PAD * 24 + (size_t)g.tile_len * 8;
-  if (smem > 100 * 1024)
-    return fail(ctx, LCS_ERR_RANGE, "xcorr plan: frequency grid too sparse for one shared-memory tile (spread too large)");
-
-  LCS_CUDA(ctx, p->d_w01.alloc(w01.size()));
-  LCS_CUDA(ctx, p->d_w2.alloc(w2.size()));
-  LCS_CUDA(ctx, p->d_soff.alloc(soff.size()));
-  LCS_CUDA(ctx, p->d_smin.alloc(smin.size()));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_w01.p, w01.data(), w01.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_w2.p, w2.data(), w2.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_soff.p, soff.data(), soff.size() * sizeof(int), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, cudaMemcpy(p->d_smin.p, smin.data(), smin.size() * sizeof(int), cudaMemcpyHostToDevice));
-  LCS_CUDA(ctx, p->d_sp_partial.alloc((size_t)max_batch * g.n_comb_sp * LCS_N_FOLD));
-  lcs_status st = tc_plan_setup(p.get());
-  if (st != LCS_OK) return st;
+  std::vector<PlanCfg> cfg(1);
+  cfg[0].fc_req = fc_req;
+  cfg[0].fc_prog = fc_prog;
+  cfg[0].fs_prog = fs_prog;
+  cfg[0].f.assign(f_search_set, f_search_set + n_f);
+  cudaStream_t st = ctx->streams[0];
+  lcs_status rc = planset_build(ctx, p->ps, n_cap, arm, cfg, true, st);
+  if (rc != LCS_OK) return rc;
+  LCS_CUDA(ctx, p->d_sp_partial.alloc((size_t)max_batch * p->ps.geom.n_comb_sp * LCS_N_FOLD));
+  // the plan is used from arbitrary streams afterwards: finish the build here and read the builder's diagnostics
+  int flag = 0;
+  LCS_CUDA(ctx, cudaMemcpyAsync(&flag, p->ps.d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+  LCS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (flag) { p->ps.tc_ready = false; p->ps.tc_why = "template digits outside the exact range of the integer formulation"; }
   *out = p.release();
   return LCS_OK;
 }
 
-static int resolve_kernel(const lcs_xcorr_plan* p, int iq_format) {
-  if (p->kernel == LCS_KERNEL_FP32) return LCS_KERNEL_FP32;
-  if (p->kernel == LCS_KERNEL_TC) return LCS_KERNEL_TC;
-  // AUTO: the tensor-core kernel is exact only for 8-bit IQ; its cost is flat in n_f (one 128-row M tile per <=42
-  // hypotheses) while the FP32 kernel's is proportional to n_f, so tiny grids (tracker mode, n_f=1) stay on FP32.
-  return (iq_format == LCS_IQ_CU8 && p->tc_ready && p->geom.n_f >= 4) ? LCS_KERNEL_TC : LCS_KERNEL_FP32;
+static lcs_status run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single,
+                             double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial, cudaStream_t st) {
+  lcs_ctx* ctx = p->ctx;
+  if (batch == 0 || batch > p->max_batch) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: batch exceeds plan max_batch");
+  if (!p->timing)
+    return planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st);
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (p->ev_pool.empty()) {
+    LCS_CUDA(ctx, cudaEventCreate(&ev.first));
+    LCS_CUDA(ctx, cudaEventCreate(&ev.second));
+  } else {
+    ev = p->ev_pool.back();
+    p->ev_pool.pop_back();
+  }
+  lcs_status rc = planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st, &ev);
+  if (rc != LCS_OK) { p->ev_pool.push_back(ev); return rc; }     // nothing usable was recorded
+  p->ev_used.push_back(ev);
+  return LCS_OK;
 }
 
-static lcs_status run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single,
-                             double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st) {
-  lcs_ctx* ctx = p->ctx;
-  if (!d_iq || !d_single || !d_pow || !d_frq || !d_spi) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: null pointer");
-  if (batch == 0 || batch > p->max_batch) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: batch exceeds plan max_batch");
-  if (iq_format != LCS_IQ_CF32 && iq_format != LCS_IQ_CU8 && iq_format != LCS_IQ_C128)
-    return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: bad iq_format");
-  const int kern = resolve_kernel(p, iq_format);
-  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  if (p->timing) {
-    if (p->ev_pool.empty()) {
-      LCS_CUDA(ctx, cudaEventCreate(&ev.first));
-      LCS_CUDA(ctx, cudaEventCreate(&ev.second));
-    } else {
-      ev = p->ev_pool.back();
-      p->ev_pool.pop_back();
-    }
-    LCS_CUDA(ctx, cudaEventRecord(ev.first, st));
-  }
-  if (kern == LCS_KERNEL_TC) {
-    if (iq_format != LCS_IQ_CU8) return fail(ctx, LCS_ERR_ARG, "tensor-core correlator needs LCS_IQ_CU8 input");
-    if (!p->tc_ready) return fail(ctx, LCS_ERR_STATE, "tensor-core correlator not available for this plan");
-    ctx->launches += launch_xcorr_fold_tc(p, d_iq, batch, d_single, st);
-  } else {
-    ctx->launches += launch_xcorr_fold_fp32(p->geom, d_iq, iq_format, batch, p->d_w01.p, p->d_w2.p, p->d_soff.p,
-                                            p->d_smin.p, d_single, st);
-  }
-  if (p->timing) {
-    LCS_CUDA(ctx, cudaEventRecord(ev.second, st));
-    p->ev_used.push_back(ev);
-  }
-  ctx->launches += launch_sp_partial(p->geom, d_iq, iq_format, batch, p->d_sp_partial.p, st);
-  ctx->launches += launch_epilogue(p->geom, batch, d_single, p->d_sp_partial.p, d_pow, d_frq, d_spi, d_inc, st);
-  LCS_CUDA(ctx, cudaGetLastError());
-  return LCS_OK;
+lcs_status plan_run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single, double* d_pow,
+                           int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial, cudaStream_t st) {
+  return run_device(p, d_iq, iq_format, batch, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 8-bit exactness probe of the c128 drop-in call: a capture read from an rtl-sdr dump holds exactly (u8-127)/128
+// (src/capbuf.cpp:172-175).  If every component of the buffer is such a value the raw bytes are reconstructed and the
+// tensor-core correlator (exact for 8-bit IQ) serves the call; anything else stays on the FP32 correlator.
+// ---------------------------------------------------------------------------------------------
+__global__ void c128_to_cu8_kernel(const double* __restrict__ cap, const uint32_t n, unsigned char* __restrict__ cu8, int* __restrict__ inexact) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = cap[i] * 128.0 + 127.0;         // exact for the values in question
+  const double r = rint(v);
+  if (!(v == r) || r < 0.0 || r > 255.0) { atomicOr(inexact, 1); return; }
+  cu8[i] = (unsigned char)(int)r;
 }
 
 }  // namespace lcs
@@ -170,7 +99,7 @@ using namespace lcs;
 
 extern "C" {
 
-const char* lcs_version(void) { return "lcs_b200 0.1 (sm_100a)"; }
+const char* lcs_version(void) { return "lcs_b200 0.2 (sm_100a)"; }
 
 lcs_status lcs_ctx_create(int device, lcs_ctx** out) {
   if (!out) return fail(nullptr, LCS_ERR_ARG, "ctx_create: null out pointer");
@@ -187,16 +116,39 @@ lcs_status lcs_ctx_create(int device, lcs_ctx** out) {
     return fail(nullptr, LCS_ERR_CUDA, "device is not compute capability 10.x (kernels are built for sm_100a only)");
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(nullptr, LCS_ERR_CUDA, cudaGetErrorString(e));
-  lcs_ctx* c = new lcs_ctx();
+  std::unique_ptr<lcs_ctx> c(new lcs_ctx());
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 2; i++)
     if (cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
-      delete c;
+      for (int k = 0; k < i; k++) cudaStreamDestroy(c->streams[k]);
       return fail(nullptr, LCS_ERR_CUDA, "stream creation failed");
     }
+  // constants of the plan builder: the three time-domain PSS (lte_lib.cpp:177-188) and the fixed-point scale of the
+  // tensor-core templates.  A frequency shift only rotates a tap, so |component| <= |pss_td tap| / 137 for every offset:
+  // one power of two S serves all plans.
+  cd td[3][137];
+  double maxmag = 0;
+  for (int t = 0; t < 3; t++) {
+    pss_td(t, td[t]);
+    for (int k = 0; k < 137; k++) maxmag = std::max(maxmag, std::abs(td[t][k]) / 137.0);
   }
-  *out = c;
+  const double limit = 127.0 * 65536 + 127 * 256 + 127;
+  int ex = (int)std::floor(std::log2(limit / maxmag));
+  while (std::ldexp(maxmag, ex) > limit) ex--;
+  c->tc_scale = std::ldexp(1.0, ex);
+  if (c->d_pss_td.alloc(3 * 137 * 2) != cudaSuccess ||
+      cudaMemcpy(c->d_pss_td.p, &td[0][0], sizeof(td), cudaMemcpyHostToDevice) != cudaSuccess) {
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(c->streams[i]);
+    return fail(nullptr, LCS_ERR_CUDA, "pss_td upload failed");
+  }
+  xcorr_fp32_init();
+  lcs_status rc = tc_init(c.get());
+  if (rc != LCS_OK) {
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(c->streams[i]);
+    return rc;
+  }
+  *out = c.release();
   return LCS_OK;
 }
 
@@ -204,7 +156,7 @@ void lcs_ctx_destroy(lcs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (auto* p : ctx->cached_plans) delete p;
+  for (auto* p : ctx->cached_plans) lcs_xcorr_plan_destroy(p);
   ctx->cached_plans.clear();
   chain_scratch_release(ctx);
   for (int i = 0; i < 2; i++)
@@ -274,16 +226,16 @@ lcs_status lcs_xcorr_plan_timing_read(lcs_xcorr_plan* p, double* kernel_ms, uint
   return LCS_OK;
 }
 
-uint16_t lcs_xcorr_plan_n_comb_xc(const lcs_xcorr_plan* p) { return p ? (uint16_t)p->geom.n_comb_xc : 0; }
-uint16_t lcs_xcorr_plan_n_comb_sp(const lcs_xcorr_plan* p) { return p ? (uint16_t)p->geom.n_comb_sp : 0; }
-int lcs_xcorr_plan_kernel(const lcs_xcorr_plan* p, int iq_format) { return p ? resolve_kernel(p, iq_format) : 0; }
+uint16_t lcs_xcorr_plan_n_comb_xc(const lcs_xcorr_plan* p) { return p ? (uint16_t)p->ps.geom.n_comb_xc : 0; }
+uint16_t lcs_xcorr_plan_n_comb_sp(const lcs_xcorr_plan* p) { return p ? (uint16_t)p->ps.geom.n_comb_sp : 0; }
+int lcs_xcorr_plan_kernel(const lcs_xcorr_plan* p, int iq_format) { return p ? planset_resolve_kernel(p->ps, p->kernel, iq_format) : 0; }
 
 lcs_status lcs_xcorr_pss_device(lcs_xcorr_plan* plan, const void* d_iq, int iq_format, uint32_t batch,
                                 float* d_single_planar, double* d_pow, int32_t* d_frq, double* d_sp_incoherent,
                                 float* d_incoherent_planar, void* stream) {
   if (!plan) return fail(nullptr, LCS_ERR_ARG, "xcorr_pss_device: null plan");
   return run_device(plan, d_iq, iq_format, batch, d_single_planar, d_pow, d_frq, d_sp_incoherent, d_incoherent_planar,
-                    (cudaStream_t)stream);
+                    plan->d_sp_partial.p, (cudaStream_t)stream);
 }
 
 // Host-buffer batched call: chunks of the batch alternate between the context's two streams so
@@ -294,14 +246,16 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
   lcs_ctx* ctx = p->ctx;
   if (!h_iq || !h_pow || !h_frq || !h_spi) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_batch_host: null pointer");
   if (batch == 0) return LCS_OK;
-  const XcorrGeom& g = p->geom;
+  const XcorrGeom& g = p->ps.geom;
   const size_t samp_bytes = iq_format == LCS_IQ_CU8 ? 2 : (iq_format == LCS_IQ_CF32 ? 8 : (iq_format == LCS_IQ_C128 ? 16 : 0));
   if (!samp_bytes) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_batch_host: bad iq_format");
   LCS_CUDA(ctx, cudaSetDevice(ctx->device));
-  const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, 8u), batch);
-  const size_t n_single = (size_t)3 * g.n_f * LCS_N_FOLD;
+  // chunk: large enough that the persistent correlator CTAs get several tiles each (32 buffers = 8 tiles per CTA), small
+  // enough that the copies of neighbouring chunks overlap the kernels
+  const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, 32u), batch);
+  const size_t n_single = (size_t)3 * g.n_f_stride * LCS_N_FOLD;
   for (int s = 0; s < 2; s++) {
-    LCS_CUDA(ctx, p->hb[s].iq.ensure((size_t)chunk * g.n_cap * 16));
+    LCS_CUDA(ctx, p->hb[s].iq.ensure((size_t)chunk * g.n_cap * samp_bytes + 16));
     LCS_CUDA(ctx, p->hb[s].single.ensure(chunk * n_single));
     LCS_CUDA(ctx, p->hb[s].pow.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, p->hb[s].frq.ensure((size_t)chunk * 3 * LCS_N_FOLD));
@@ -315,11 +269,7 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
     auto& hb = p->hb[s];
     LCS_CUDA(ctx, cudaMemcpyAsync(hb.iq.p, (const char*)h_iq + (size_t)b0 * g.n_cap * samp_bytes,
                                   (size_t)nb * g.n_cap * samp_bytes, cudaMemcpyHostToDevice, st));
-    // each stream needs its own sp_partial scratch
-    double* saved = p->d_sp_partial.p;
-    p->d_sp_partial.p = hb.sp_partial.p;
-    lcs_status rc = run_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, st);
-    p->d_sp_partial.p = saved;
+    lcs_status rc = run_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, hb.sp_partial.p, st);
     if (rc != LCS_OK) return rc;
     if (h_single)
       LCS_CUDA(ctx, cudaMemcpyAsync(h_single + (size_t)b0 * n_single, hb.single.p, (size_t)nb * n_single * 4, cudaMemcpyDeviceToHost, st));
@@ -343,7 +293,7 @@ lcs_status lcs_xcorr_pss(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap, con
   lcs_xcorr_plan* p = nullptr;
   lcs_status rc = get_cached_plan(ctx, n_cap, f_search_set, n_f, ds_comb_arm, fc_requested, fc_programmed, fs_programmed, &p);
   if (rc != LCS_OK) return rc;
-  const XcorrGeom& g = p->geom;
+  const XcorrGeom& g = p->ps.geom;
   cudaStream_t st = ctx->streams[0];
   const size_t n_single = (size_t)3 * n_f * LCS_N_FOLD;
   LCS_CUDA(ctx, ctx->d_capbuf.ensure((size_t)n_cap * 2));
@@ -353,9 +303,24 @@ lcs_status lcs_xcorr_pss(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap, con
   LCS_CUDA(ctx, ctx->d_pow.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_frq.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_spi.ensure(LCS_N_FOLD));
+  LCS_CUDA(ctx, ctx->d_spp.ensure((size_t)g.n_comb_sp * LCS_N_FOLD));
   LCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_capbuf.p, capbuf, (size_t)n_cap * 16, cudaMemcpyHostToDevice, st));
-  rc = run_device(p, ctx->d_capbuf.p, LCS_IQ_C128, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p,
-                  incoherent ? ctx->d_inc.p : nullptr, st);
+  // 8-bit exact input (an rtl-sdr capture, capbuf.cpp:172-175) goes to the tensor-core correlator
+  const void* d_in = ctx->d_capbuf.p;
+  int fmt = LCS_IQ_C128;
+  if (planset_resolve_kernel(p->ps, p->kernel, LCS_IQ_CU8) == LCS_KERNEL_TC) {
+    int inexact = 0;
+    LCS_CUDA(ctx, ctx->d_cu8.ensure((size_t)n_cap * 2 + 16));
+    LCS_CUDA(ctx, ctx->d_flag8.ensure(1));
+    LCS_CUDA(ctx, cudaMemsetAsync(ctx->d_flag8.p, 0, 4, st));
+    c128_to_cu8_kernel<<<(2 * n_cap + 255) / 256, 256, 0, st>>>(ctx->d_capbuf.p, 2 * n_cap, ctx->d_cu8.p, ctx->d_flag8.p);
+    ctx->launches++;
+    LCS_CUDA(ctx, cudaMemcpyAsync(&inexact, ctx->d_flag8.p, 4, cudaMemcpyDeviceToHost, st));
+    LCS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!inexact) { d_in = ctx->d_cu8.p; fmt = LCS_IQ_CU8; }
+  }
+  rc = run_device(p, d_in, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p,
+                  incoherent ? ctx->d_inc.p : nullptr, ctx->d_spp.p, st);
   if (rc != LCS_OK) return rc;
   // reference layouts: vf3d [t][idx][f]; mat(3,9600) column-major
   ctx->launches += launch_planar_to_ref(g, ctx->d_single.p, ctx->d_ref.p, st);
@@ -374,7 +339,7 @@ lcs_status lcs_xcorr_pss(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap, con
     const size_t n_xc = (size_t)3 * (n_cap - 136) * n_f;
     DevBuf<float2> d_xc;
     LCS_CUDA(ctx, d_xc.alloc(n_xc));
-    ctx->launches += launch_xc_debug(g, ctx->d_capbuf.p, LCS_IQ_C128, p->d_w01.p, p->d_w2.p, d_xc.p, st);
+    ctx->launches += launch_xc_debug(g, ctx->d_capbuf.p, LCS_IQ_C128, p->ps.d_w01.p, p->ps.d_w2.p, d_xc.p, st);
     LCS_CUDA(ctx, cudaMemcpyAsync(xc, d_xc.p, n_xc * 8, cudaMemcpyDeviceToHost, st));
     LCS_CUDA(ctx, cudaStreamSynchronize(st));
   }
@@ -402,26 +367,20 @@ namespace lcs {
 lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_set, uint32_t n_f, uint8_t arm,
                            double fc_req, double fc_prog, double fs_prog, lcs_xcorr_plan** out) {
   for (auto* q : ctx->cached_plans) {
-    if (q->geom.n_cap == n_cap && q->geom.n_f == n_f && q->geom.ds_comb_arm == arm && q->fc_requested == fc_req &&
-        q->fc_programmed == fc_prog && q->fs_programmed == fs_prog &&
-        std::memcmp(q->f_search_set.data(), f_search_set, n_f * sizeof(double)) == 0) {
+    const PlanCfg& c = q->ps.cfg[0];
+    if (q->ps.geom.n_cap == n_cap && c.f.size() == n_f && q->ps.geom.ds_comb_arm == arm && c.fc_req == fc_req &&
+        c.fc_prog == fc_prog && c.fs_prog == fs_prog && std::memcmp(c.f.data(), f_search_set, n_f * sizeof(double)) == 0) {
       *out = q;
       return LCS_OK;
     }
   }
   lcs_xcorr_plan* p = nullptr;
-  static const bool trace = std::getenv("LCS_TRACE_PLANS") != nullptr;     // debug aid: host cost of plan turnover
-  const auto t0 = std::chrono::steady_clock::now();
   lcs_status rc = build_plan(ctx, n_cap, f_search_set, n_f, arm, fc_req, fc_prog, fs_prog, 1, LCS_KERNEL_AUTO, &p);
   if (rc != LCS_OK) return rc;
-  const auto t1 = std::chrono::steady_clock::now();
   if (ctx->cached_plans.size() >= 8) {
-    delete ctx->cached_plans.front();
+    lcs_xcorr_plan_destroy(ctx->cached_plans.front());
     ctx->cached_plans.erase(ctx->cached_plans.begin());
   }
-  if (trace)
-    std::fprintf(stderr, "[lcs] plan build %.3f ms, evict %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   ctx->cached_plans.push_back(p);
   *out = p;
   return LCS_OK;

@@ -35,7 +35,7 @@ __device__ __forceinline__ void argmax_combine(double& v, int& i, double v2, int
 __global__ void __launch_bounds__(PK_THREADS) peak_search_kernel(const double* __restrict__ pow_all, const int32_t* __restrict__ frq_all,
                                                                  const double* __restrict__ spi_all, const float* __restrict__ single_all,
                                                                  double* __restrict__ work_all, DevPeak* __restrict__ peaks_all,
-                                                                 int32_t* __restrict__ npeaks_all, uint32_t n_f, double r_th1,
+                                                                 int32_t* __restrict__ npeaks_all, uint32_t n_f /* stride */, double r_th1,
                                                                  double rx_cutoff, double n_comb, double box, int arm, double cancel,
                                                                  int max_peaks) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,11 +117,11 @@ __global__ void __launch_bounds__(PK_THREADS) peak_search_kernel(const double* _
 static lcs_status launch_peak_search(lcs_xcorr_plan* p, uint32_t nb, const double* d_pow, const int32_t* d_frq, const double* d_spi,
                                      const float* d_single, double* d_work, DevPeak* d_peaks, int32_t* d_npeaks, int max_peaks,
                                      cudaStream_t st) {
-  const XcorrGeom& g = p->geom;
+  const XcorrGeom& g = p->ps.geom;
   const double r_th1 = chi2cdf_inv(1 - std::pow(10.0, -12.0), 2.0 * g.n_comb_xc * (2 * g.ds_comb_arm + 1));
   const double rx_cutoff = (6 * 12 * 15e3 / 2 + 4 * 15e3) / ((30720000.0 / 16) / 2);
   const double cancel = std::pow(10.0, -12.0 / 10.0);
-  peak_search_kernel<<<nb, PK_THREADS, 0, st>>>(d_pow, d_frq, d_spi, d_single, d_work, d_peaks, d_npeaks, g.n_f, r_th1, rx_cutoff,
+  peak_search_kernel<<<nb, PK_THREADS, 0, st>>>(d_pow, d_frq, d_spi, d_single, d_work, d_peaks, d_npeaks, g.n_f_stride, r_th1, rx_cutoff,
                                                 (double)g.n_comb_xc, (double)(2 * g.ds_comb_arm + 1), (int)g.ds_comb_arm, cancel,
                                                 max_peaks);
   p->ctx->launches++;
@@ -137,16 +137,17 @@ constexpr uint32_t SEARCH_CHUNK = 32;
 template <class F>
 static lcs_status search_batch(lcs_xcorr_plan* p, const void* h_iq, int iq_format, uint32_t batch, F&& per_buffer) {
   lcs_ctx* ctx = p->ctx;
-  const XcorrGeom& g = p->geom;
+  const XcorrGeom& g = p->ps.geom;
+  const PlanCfg& cfg = p->ps.cfg[0];
   const size_t samp_bytes = iq_format == LCS_IQ_CU8 ? 2 : (iq_format == LCS_IQ_CF32 ? 8 : (iq_format == LCS_IQ_C128 ? 16 : 0));
   if (!samp_bytes) return fail(ctx, LCS_ERR_ARG, "search_batch: bad iq_format");
   if (batch == 0) return LCS_OK;
   LCS_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, SEARCH_CHUNK), batch);
-  const size_t n_single = (size_t)3 * g.n_f * LCS_N_FOLD;
+  const size_t n_single = (size_t)3 * g.n_f_stride * LCS_N_FOLD;
   for (int s = 0; s < 2; s++) {
     auto& hb = p->hb[s];
-    LCS_CUDA(ctx, hb.iq.ensure((size_t)chunk * g.n_cap * 16));
+    LCS_CUDA(ctx, hb.iq.ensure((size_t)chunk * g.n_cap * samp_bytes + 16));
     LCS_CUDA(ctx, hb.single.ensure(chunk * n_single));
     LCS_CUDA(ctx, hb.pow.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.frq.ensure((size_t)chunk * 3 * LCS_N_FOLD));
@@ -168,10 +169,7 @@ static lcs_status search_batch(lcs_xcorr_plan* p, const void* h_iq, int iq_forma
     auto& hb = p->hb[s];
     LCS_CUDA(ctx, cudaMemcpyAsync(hb.iq.p, (const char*)h_iq + (size_t)b0 * g.n_cap * samp_bytes, (size_t)nb * g.n_cap * samp_bytes,
                                   cudaMemcpyHostToDevice, st));
-    double* saved = p->d_sp_partial.p;        // each stream needs its own sp_partial scratch
-    p->d_sp_partial.p = hb.sp_partial.p;
-    lcs_status rc = lcs_xcorr_pss_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, st);
-    p->d_sp_partial.p = saved;
+    lcs_status rc = plan_run_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, hb.sp_partial.p, st);
     if (rc != LCS_OK) return rc;
     rc = launch_peak_search(p, nb, hb.pow.p, hb.frq.p, hb.spi.p, hb.single.p, hb.work.p, reinterpret_cast<DevPeak*>(hb.peaks.p),
                             hb.npeaks.p, SEARCH_MAX_PEAKS, st);
@@ -197,19 +195,19 @@ static lcs_status search_batch(lcs_xcorr_plan* p, const void* h_iq, int iq_forma
         LCS_CUDA(ctx, cudaMemcpy(spi.data(), hb.spi.p + (size_t)i * LCS_N_FOLD, spi.size() * 8, cudaMemcpyDeviceToHost));
         LCS_CUDA(ctx, cudaMemcpy(sg.data(), hb.single.p + (size_t)i * n_single, n_single * 4, cudaMemcpyDeviceToHost));
         calc_z_th1(spi.data(), LCS_N_FOLD, (uint16_t)g.n_comb_xc, (uint8_t)g.ds_comb_arm, z.data());
-        auto at = [&](int t, int f, int idx) { return sg[((size_t)t * g.n_f + f) * LCS_N_FOLD + idx]; };
-        peak_search(pw.data(), fq.data(), z.data(), p->f_search_set.data(), p->fc_requested, p->fc_programmed, at,
+        auto at = [&](int t, int f, int idx) { return sg[((size_t)t * g.n_f_stride + f) * LCS_N_FOLD + idx]; };
+        peak_search(pw.data(), fq.data(), z.data(), cfg.f.data(), cfg.fc_req, cfg.fc_prog, at,
                     (uint8_t)g.ds_comb_arm, pk);
       } else {
         for (int k = 0; k < h_np[s][i]; k++) {
           const DevPeak& d = h_peaks[s][(size_t)i * SEARCH_MAX_PEAKS + k];
           lcs_cell c;
           lcs_cell_init(&c);
-          c.fc_requested = p->fc_requested;
-          c.fc_programmed = p->fc_programmed;
+          c.fc_requested = cfg.fc_req;
+          c.fc_programmed = cfg.fc_prog;
           c.pss_pow = d.pss_pow;
           c.ind = d.ind;
-          c.freq = p->f_search_set[d.fi];
+          c.freq = cfg.f[d.fi];
           c.n_id_2 = (int8_t)d.row;
           pk.push_back(c);
         }
@@ -259,7 +257,8 @@ lcs_status lcs_cell_search_batch_cu8(lcs_xcorr_plan* p, const uint8_t* iq_host, 
   lcs_ctx* ctx = p->ctx;
   return search_batch(p, iq_host, LCS_IQ_CU8, batch, [&](uint32_t b, const void* d_cap, const std::vector<lcs_cell>& pk) {
     uint32_t found = 0;
-    lcs_status rc = cell_chain_dev(ctx, d_cap, LCS_IQ_CU8, p->geom.n_cap, pk, p->fc_requested, p->fc_programmed, p->fs_programmed,
+    const PlanCfg& cfg = p->ps.cfg[0];
+    lcs_status rc = cell_chain_dev(ctx, d_cap, LCS_IQ_CU8, p->ps.geom.n_cap, pk, cfg.fc_req, cfg.fc_prog, cfg.fs_prog,
                                    cells ? cells + (size_t)b * max_cells : nullptr, max_cells, &found);
     n_cells[b] = found;
     return rc;

@@ -62,17 +62,27 @@ __device__ __forceinline__ void cmac(float2& acc, const float wx, const float wy
 
 template <int FMT, int FW>
 __global__ void __launch_bounds__(XC_THREADS, 2)
-xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w01g, const float2* __restrict__ w2g,
-                       const int* __restrict__ soff, const int* __restrict__ smin_tab, float* __restrict__ single_planar,
-                       const uint32_t n_cap, const uint32_t n_f, const uint32_t n_comb, const uint32_t n_fchunk,
+xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w01g_all, const float2* __restrict__ w2g_all,
+                       const int* __restrict__ soff_all, const int* __restrict__ smin_all, float* __restrict__ single_planar,
+                       const int* __restrict__ plan_nf, const uint32_t* __restrict__ buf_plan,
+                       const uint32_t n_cap, const uint32_t n_f_stride, const uint32_t n_comb, const uint32_t n_fchunk,
                        const uint32_t tile_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* w01s = reinterpret_cast<float4*>(smem_raw);                        // [FW][NTAP_PAD] roots 0,1
   float2* w2s = reinterpret_cast<float2*>(w01s + FW * XC_NTAP_PAD);          // [FW][NTAP_PAD] root 2
-  float2* tile = w2s + FW * XC_NTAP_PAD;                                     // [tile_len]
+  float* part = reinterpret_cast<float*>(w2s + FW * XC_NTAP_PAD);            // [42][XC_THREADS] second-level partial sums
+  float2* tile = reinterpret_cast<float2*>(part + 6 * XC_R * XC_THREADS);    // [tile_len]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t fchunk = blockIdx.y, b = blockIdx.z;
+  // operands of this buffer's plan
+  const uint32_t plan = buf_plan ? __ldg(buf_plan + b) : 0u;
+  const uint32_t n_f = (uint32_t)__ldg(plan_nf + plan);
+  if (fchunk * FW >= n_f) return;                                            // block-uniform: this plan has fewer hypotheses
+  const float4* w01g = w01g_all + (size_t)plan * n_f_stride * XC_NTAP_PAD;
+  const float2* w2g = w2g_all + (size_t)plan * n_f_stride * XC_NTAP_PAD;
+  const int* soff = soff_all + (size_t)plan * n_comb * n_f_stride;
+  const int* smin_tab = smin_all + (size_t)plan * n_comb * n_fchunk;
   // warp -> (hypothesis fsub of the chunk, lag sub-tile lsub of the block)
   const int fsub = warp % FW, lsub = warp / FW;
   const uint32_t f = fchunk * FW + fsub;
@@ -101,7 +111,7 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
 
   for (uint32_t m = 0; m < n_comb; m++) {
     const int smin = __ldg(smin_tab + m * n_fchunk + fchunk);
-    const int off = __ldg(soff + m * n_f + fcl) - smin;
+    const int off = __ldg(soff + m * n_f_stride + fcl) - smin;
     __syncthreads();  // everyone is done with the previous tile (and, for m==0, the W stores are issued)
     for (uint32_t e = tid; e < tile_len; e += XC_THREADS) {
       const size_t g = (size_t)i0_blk + smin + e;
@@ -119,21 +129,40 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
 #pragma unroll
     for (int j = 0; j < XC_R - 1; j++) win[j] = xp[j];
 
+    // Two-level summation: the 140 taps are accumulated in blocks of XC_TAP_BLOCK = 28; after each block the 42 register
+    // accumulators are added into per-thread partial sums in shared memory and cleared.  The rounding error of an FP32
+    // chain grows with the magnitude of its running sum, so five short chains plus five adds are ~2x more accurate than
+    // one chain of 274 FMAs (measured margin to the 1e-6 contract in DESIGN.md) for ~5 % more instructions.
+    float* mypart = part + tid;
 #pragma unroll 1
-    for (int tb = 0; tb < XC_NTAP_PAD; tb += XC_R) {
+    for (int tb0 = 0; tb0 < XC_NTAP_PAD; tb0 += XC_TAP_BLOCK) {
+#pragma unroll 1
+      for (int tb = tb0; tb < tb0 + XC_TAP_BLOCK; tb += XC_R) {
 #pragma unroll
-      for (int u = 0; u < XC_R; u++) {
-        win[(u + XC_R - 1) % XC_R] = xp[tb + u + XC_R - 1];
-        const float4 wa = w01w[tb + u];
-        const float2 wb = w2w[tb + u];
+        for (int u = 0; u < XC_R; u++) {
+          win[(u + XC_R - 1) % XC_R] = xp[tb + u + XC_R - 1];
+          const float4 wa = w01w[tb + u];
+          const float2 wb = w2w[tb + u];
 #pragma unroll
-        for (int j = 0; j < XC_R; j++) {
-          const float2 x = win[(u + j) % XC_R];
-          cmac(acc[0][j], wa.x, wa.y, x);
-          cmac(acc[1][j], wa.z, wa.w, x);
-          cmac(acc[2][j], wb.x, wb.y, x);
+          for (int j = 0; j < XC_R; j++) {
+            const float2 x = win[(u + j) % XC_R];
+            cmac(acc[0][j], wa.x, wa.y, x);
+            cmac(acc[1][j], wa.z, wa.w, x);
+            cmac(acc[2][j], wb.x, wb.y, x);
+          }
         }
       }
+      const bool first = tb0 == 0, last = tb0 + XC_TAP_BLOCK >= XC_NTAP_PAD;
+#pragma unroll
+      for (int t = 0; t < 3; t++)
+#pragma unroll
+        for (int j = 0; j < XC_R; j++) {
+          float* q = mypart + ((t * XC_R + j) * 2) * XC_THREADS;
+          float2 s = acc[t][j];
+          if (!first) { s.x = __fadd_rn(q[0], s.x); s.y = __fadd_rn(q[XC_THREADS], s.y); }
+          if (!last) { q[0] = s.x; q[XC_THREADS] = s.y; acc[t][j] = make_float2(0.f, 0.f); }
+          else acc[t][j] = s;
+        }
     }
     // IT++ sqr(complex<float>) then float += : re*re+im*im, un-fused  (searcher.cpp:300)
 #pragma unroll
@@ -147,7 +176,7 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
     const float ncf = (float)n_comb;
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-      float* dst = single_planar + (((size_t)b * 3 + t) * n_f + f) * LCS_N_FOLD;
+      float* dst = single_planar + (((size_t)b * 3 + t) * n_f_stride + f) * LCS_N_FOLD;
 #pragma unroll
       for (int j = 0; j < XC_R; j++) {
         const uint32_t idx = i0 + lane * XC_R + j;
@@ -157,16 +186,26 @@ xcorr_fold_fp32_kernel(const void* __restrict__ iq, const float4* __restrict__ w
   }
 }
 
-int launch_xcorr_fold_fp32(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, const float4* d_w01,
-                           const float2* d_w2, const int* d_soff, const int* d_smin, float* d_single_planar,
-                           cudaStream_t st) {
-  const size_t smem = (size_t)g.fw * XC_NTAP_PAD * (sizeof(float4) + sizeof(float2)) + (size_t)g.tile_len * sizeof(float2);
+static size_t fp32_smem(uint32_t fw, uint32_t tile_len) {
+  return (size_t)fw * XC_NTAP_PAD * (sizeof(float4) + sizeof(float2)) + (size_t)6 * XC_R * XC_THREADS * sizeof(float) +
+         (size_t)tile_len * sizeof(float2);
+}
+void xcorr_fp32_init() {
+  const int cap = 100 * 1024;     // planset_build rejects grids that would need more
+#define SET(F, W) cudaFuncSetAttribute(xcorr_fold_fp32_kernel<F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)
+  SET(LCS_IQ_CF32, 1); SET(LCS_IQ_CF32, XC_FW); SET(LCS_IQ_CU8, 1); SET(LCS_IQ_CU8, XC_FW); SET(LCS_IQ_C128, 1); SET(LCS_IQ_C128, XC_FW);
+#undef SET
+}
+
+int launch_xcorr_fold_fp32(const XcorrGeom& g, const PlanView& pv, const void* d_iq, int iq_format, uint32_t batch,
+                           const float4* d_w01, const float2* d_w2, const int* d_soff, const int* d_smin,
+                           float* d_single_planar, cudaStream_t st) {
+  const size_t smem = fp32_smem(g.fw, g.tile_len);
   const uint32_t ti_blk = XC_TI * (XC_FW / g.fw);
   dim3 grid((LCS_N_FOLD + ti_blk - 1) / ti_blk, g.n_fchunk, batch), block(XC_THREADS);
 #define CALL_FW(F, W)                                                                                                \
-  cudaFuncSetAttribute(xcorr_fold_fp32_kernel<F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-  xcorr_fold_fp32_kernel<F, W><<<grid, block, smem, st>>>(d_iq, d_w01, d_w2, d_soff, d_smin, d_single_planar, g.n_cap, \
-                                                          g.n_f, g.n_comb_xc, g.n_fchunk, g.tile_len)
+  xcorr_fold_fp32_kernel<F, W><<<grid, block, smem, st>>>(d_iq, d_w01, d_w2, d_soff, d_smin, d_single_planar, pv.d_nf, \
+                                                          pv.d_buf_plan, g.n_cap, g.n_f_stride, g.n_comb_xc, g.n_fchunk, g.tile_len)
 #define CALL(F)                 \
   if (g.fw == 1) { CALL_FW(F, 1); } \
   else { CALL_FW(F, XC_FW); }
@@ -255,12 +294,14 @@ int launch_sp_partial(const XcorrGeom& g, const void* d_iq, int iq_format, uint3
 __global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__ single_planar,
                                                        const double* __restrict__ sp_partial, double* __restrict__ pow_out,
                                                        int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
-                                                       float* __restrict__ incoherent_planar, const uint32_t n_f,
+                                                       float* __restrict__ incoherent_planar, const uint32_t n_f_stride,
+                                                       const int* __restrict__ plan_nf, const uint32_t* __restrict__ buf_plan,
                                                        const uint32_t arm, const uint32_t n_comb_sp) {
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
   if (idx >= LCS_N_FOLD) return;
-  const float* s = single_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD;
-  float* inc_out = incoherent_planar ? incoherent_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD : nullptr;
+  const uint32_t n_f = (uint32_t)__ldg(plan_nf + (buf_plan ? __ldg(buf_plan + b) : 0u));
+  const float* s = single_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD;
+  float* inc_out = incoherent_planar ? incoherent_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD : nullptr;
   const float denom = (float)(2 * arm + 1);
   float best = 0.f;
   int best_f = 0;
@@ -293,14 +334,16 @@ template <int ARM>
 __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict__ single_planar,
                                                         const double* __restrict__ sp_partial, double* __restrict__ pow_out,
                                                         int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
-                                                        float* __restrict__ incoherent_planar, const uint32_t n_f,
+                                                        float* __restrict__ incoherent_planar, const uint32_t n_f_stride,
+                                                        const int* __restrict__ plan_nf, const uint32_t* __restrict__ buf_plan,
                                                         const uint32_t n_comb_sp) {
   constexpr uint32_t NQ = LCS_N_FOLD / 4;
   const uint32_t q = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
   if (q >= NQ) return;
+  const uint32_t n_f = (uint32_t)__ldg(plan_nf + (buf_plan ? __ldg(buf_plan + b) : 0u));
   const uint32_t qp = q == 0 ? NQ - 1 : q - 1, qn = q == NQ - 1 ? 0 : q + 1;
-  const float4* s = reinterpret_cast<const float4*>(single_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD);
-  float4* inc_out = incoherent_planar ? reinterpret_cast<float4*>(incoherent_planar + ((size_t)b * 3 + t) * n_f * LCS_N_FOLD) : nullptr;
+  const float4* s = reinterpret_cast<const float4*>(single_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD);
+  float4* inc_out = incoherent_planar ? reinterpret_cast<float4*>(incoherent_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD) : nullptr;
   const float denom = (float)(2 * ARM + 1);
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int best_f[4] = {0, 0, 0, 0};
@@ -343,13 +386,13 @@ __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict_
   }
 }
 
-int launch_epilogue(const XcorrGeom& g, uint32_t batch, const float* d_single_planar, const double* d_sp_partial,
-                    double* d_pow, int32_t* d_frq, double* d_sp_incoherent, float* d_incoherent_planar,
-                    cudaStream_t st) {
+int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, const float* d_single_planar,
+                    const double* d_sp_partial, double* d_pow, int32_t* d_frq, double* d_sp_incoherent,
+                    float* d_incoherent_planar, cudaStream_t st) {
   if (g.ds_comb_arm <= 4) {
     dim3 grid((LCS_N_FOLD / 4 + 127) / 128, 3, batch);
 #define EPI(A) epilogue4_kernel<A><<<grid, 128, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent, \
-                                                     d_incoherent_planar, g.n_f, g.n_comb_sp)
+                                                     d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan, g.n_comb_sp)
     switch (g.ds_comb_arm) {
       case 0: EPI(0); break;
       case 1: EPI(1); break;
@@ -362,7 +405,7 @@ int launch_epilogue(const XcorrGeom& g, uint32_t batch, const float* d_single_pl
   }
   dim3 grid((LCS_N_FOLD + 255) / 256, 3, batch);
   epilogue_kernel<<<grid, 256, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent,
-                                        d_incoherent_planar, g.n_f, g.ds_comb_arm, g.n_comb_sp);
+                                        d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan, g.ds_comb_arm, g.n_comb_sp);
   return 1;
 }
 
@@ -384,8 +427,8 @@ __global__ void planar_to_ref_kernel(const float* __restrict__ planar, float* __
   }
 }
 int launch_planar_to_ref(const XcorrGeom& g, const float* d_planar, float* d_ref, cudaStream_t st) {
-  dim3 grid((LCS_N_FOLD + 31) / 32, (g.n_f + 31) / 32, 3), block(32, 8);
-  planar_to_ref_kernel<<<grid, block, 0, st>>>(d_planar, d_ref, g.n_f);
+  dim3 grid((LCS_N_FOLD + 31) / 32, (g.n_f_stride + 31) / 32, 3), block(32, 8);
+  planar_to_ref_kernel<<<grid, block, 0, st>>>(d_planar, d_ref, g.n_f_stride);
   return 1;
 }
 
@@ -413,8 +456,8 @@ __global__ void __launch_bounds__(128) xc_debug_kernel(const void* __restrict__ 
 }
 int launch_xc_debug(const XcorrGeom& g, const void* d_iq, int iq_format, const float4* d_w01, const float2* d_w2,
                     float2* d_xc, cudaStream_t st) {
-  dim3 grid((g.n_cap - 136 + 127) / 128, g.n_f);
-#define CALL(F) xc_debug_kernel<F><<<grid, 128, 0, st>>>(d_iq, d_w01, d_w2, d_xc, g.n_cap, g.n_f)
+  dim3 grid((g.n_cap - 136 + 127) / 128, g.n_f_stride);
+#define CALL(F) xc_debug_kernel<F><<<grid, 128, 0, st>>>(d_iq, d_w01, d_w2, d_xc, g.n_cap, g.n_f_stride)
   LCS_DISPATCH_FMT(iq_format, CALL);
 #undef CALL
   return 1;

@@ -20,6 +20,7 @@ def synth(seed, n_cap=153600):
 
 ctx = L.Context(0)
 cases = [("n_cap=29000 n_f=3", synth(1, 29000), np.array([-5000.0, 0.0, 5000.0]), 1),
+         ("n_cap=29000 n_f=19 (16,4,1)", synth(5, 29000), np.arange(-9, 10) * 5000.0, 2),
          ("n_cap=153600 n_f=7", synth(2), O.f_search_set(739e6, 20.0), 1),
          ("n_cap=153600 n_f=31 batch3", synth(3), O.f_search_set(739e6, 100.0), 3),
          ("n_cap=153600 n_f=37", synth(4), O.f_search_set(739e6, 120.0), 1)]
@@ -46,7 +47,7 @@ for name, c, f, batch in cases:
 # timing, bench shape
 import torch
 f = O.f_search_set(739e6, 100.0)
-B = 24
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 plan = ctx.plan(153600, f, 2, 739e6, 739e6, 1.92e6, max_batch=B, kernel=L.KERNEL_TC)
 iq = torch.from_numpy(np.stack([synth(100 + i) for i in range(B)])).cuda()
 single = torch.empty((B, 3, f.size, 9600), dtype=torch.float32, device="cuda")

@@ -207,7 +207,7 @@ def test_full_chain_capbuf_0000(ctx, oracle, capbuf0000, fmt):
         assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6
 
 
-def test_cellsearch_cli_full_test(tmp_path, capbuf0000):
+def test_cellsearch_cli_full_test(ctx, tmp_path, capbuf0000):
     """The reference's (commented-out) integration test, src/CMakeLists.txt:34-35:
     `CellSearch -s 739000000 -l -d test` must print `cell ID: 271`.  Run through the C++ drop-in
     (searcher.h mirror + CLI) on a capbuf_0000.it regenerated from the committed fixture."""
@@ -407,3 +407,60 @@ def test_tracker_search_cycle(ctx, lcs, capbuf0000):
     rest = ctx.tracker_search_cu8(cap, f_off, fc, fc, fs, late, tracked=[first])
     assert [c.n_id_cell() for c, _ in rest] == [c.n_id_cell() for c, _ in new if c.n_id_cell() != first]
     fr.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round-2 parity holes (VERDICT r01 "what's weak" 1, 2, 4)
+# ---------------------------------------------------------------------------------------------
+def test_tc_bench_config_vs_oracle(ctx, lcs, oracle):
+    """The configuration bench.py times (BASELINE configs[1]: n_f=31, n_cap=153600) with enough buffers that every
+    persistent CTA walks more than one work item (8 buffers): EVERY buffer against the oracle, <= 5e-7."""
+    f = lcs.f_search_set(739e6, 100.0)
+    assert f.size == 31
+    cu8 = np.stack([synth_cu8(0xC0FFEE + i) for i in range(8)])
+    _tc_vs_oracle(ctx, lcs, oracle, cu8, f, 739e6, 739e6, 1.92e6)
+
+
+def test_tc_unaligned_buffer_stride(ctx, lcs, oracle):
+    """batch > 1 with n_cap*2 % 16 != 0 (n_cap = 29004): buffers 1.. start at byte offsets that are not 16-byte aligned."""
+    f = np.arange(-3, 4) * 5000.0
+    cu8 = np.stack([synth_cu8(500 + i, 29004) for i in range(3)])
+    _tc_vs_oracle(ctx, lcs, oracle, cu8, f, 739e6, 739e6, 1.92e6)
+    cu8 = np.stack([synth_cu8(600 + i, 29001) for i in range(2)])       # odd sample count
+    _tc_vs_oracle(ctx, lcs, oracle, cu8, f, 739e6, 739e6, 1.92e6)
+
+
+def test_device_peak_search_vs_oracle(ctx, lcs, oracle, capbuf0000):
+    """Device threshold + peak_search against the ORACLE's Z_th1 + peak_search (searcher.cpp:422-510,
+    CellSearch.cpp:500-503) fed with the oracle's own xcorr_pss outputs of the same capture."""
+    fc = capbuf0000["fc"]
+    f = lcs.f_search_set(fc, 120.0)
+    real = capbuf0000["cu8"]
+    plan = ctx.plan(real.shape[0], f, 2, fc, fc, 1.92e6, max_batch=2)
+    got = plan.peaks_batch(np.stack([real, synth_cu8(0xC0FFEE)]), lcs.IQ_CU8)
+    ref = oracle.xcorr_pss(capbuf0000["capbuf"], f, 2, fc, fc, 1.92e6)
+    z = oracle.calc_Z_th1(ref["sp_incoherent"], ref["n_comb_xc"], 2)
+    o_peaks = oracle.peak_search(ref["pow"], ref["frq"], z, f, fc, fc, ref["single"], 2)
+    assert [(p.n_id_2, p.ind, p.freq) for p in got[0]] == [(p.n_id_2, p.ind, p.freq) for p in o_peaks]
+    for a, b in zip(got[0], o_peaks):
+        assert abs(a.pss_pow - b.pss_pow) < REL * o_peaks[0].pss_pow
+    assert got[1] == []
+    plan.close()
+
+
+def test_tracker_search_vs_oracle(ctx, lcs, oracle, capbuf0000):
+    """One searcher cycle (n_f = 1 at the tracked offset, searcher_thread.cpp:95-232) against the oracle's chain on the
+    same framed buffer: ids / MIB bit-exact, frame_start, freq_fine, freq_superfine as in the full-chain test."""
+    fc = capbuf0000["fc"]; fs = 1.92e6
+    f_off = 35228.0
+    cap_u8 = capbuf0000["cu8"]
+    o_cells, _ = oracle.cell_search_one(capbuf0000["capbuf"], np.array([f_off]), fc, fc, fs)
+    new = ctx.tracker_search_cu8(cap_u8, f_off, fc, fc, fs, 0.25)
+    assert len(o_cells) >= 1 and [c.n_id_cell() for c, _ in new] == [c.n_id_cell() for c in o_cells]
+    k = (fc - f_off) / fc
+    for (a, ft), b in zip(new, o_cells):
+        for key in ("n_id_1", "n_id_2", "cp_type", "ind", "n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"):
+            assert getattr(a, key) == getattr(b, key), key
+        assert abs(a.frame_start - b.frame_start) < 1e-9
+        assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6
+        assert abs(ft - (b.frame_start * (30720000.0 / 16) / (fs * k) + 0.25)) < 1e-9
