@@ -15,6 +15,8 @@
  *     (reference src/capbuf.cpp:172-175).
  *   - there is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a) and
  *     fails with LCS_ERR_CUDA when none is usable.
+ *   - threading: a context and the plans / sweep handles created from it belong to ONE host thread at a time (they
+ *     share the context's two streams and scratch buffers).  Use one context per thread; contexts are independent.
  *   - array layouts are stated per argument; "ref layout" is the reference's own
  *     (vf3d [t][idx][f]; IT++ mat/imat column-major).
  */
@@ -177,6 +179,15 @@ lcs_status lcs_cell_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t
                                lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells, lcs_cell* peaks,
                                uint32_t* n_peaks);
 
+/* kalibrate, src/LTE-Tracker.cpp:565-741: the initial search LTE-Tracker runs to calibrate the oscillator.  The grid of
+ * CellSearch.cpp:463-464 for (fc_requested, ppm) is centred on fc_requested*(correction-1) (:586-587); after the chain
+ * and dedup the strongest cell is returned in *best with *correction_residual = fc_programmed/(fc_programmed -
+ * best->freq_superfine) (:719-724; may be NULL).  *n_cells = cells that survived (0: nothing found in this buffer - the
+ * reference then captures the next one). */
+lcs_status lcs_kalibrate_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n_cap, double fc_requested,
+                             double fc_programmed, double fs_programmed, double ppm, double correction, lcs_cell* best,
+                             double* correction_residual, uint32_t* n_cells);
+
 /* ---- batched search (many capture buffers of one centre frequency, e.g. a tracked channel) ---- */
 /* xcorr_pss (searcher.cpp:389) + Z_th1 (CellSearch.cpp:500-503) + peak_search (searcher.cpp:422-510) for a batch of HOST
  * capture buffers, everything on the device: only the PSS peaks return.  iq_host is [batch][n_cap] in iq_format;
@@ -189,6 +200,30 @@ lcs_status lcs_xcorr_peaks_batch_host(lcs_xcorr_plan* plan, const void* iq_host,
  * [batch][n_cap][2]); cells is [batch][max_cells], n_cells[batch].  Same results as lcs_cell_search_cu8 per buffer. */
 lcs_status lcs_cell_search_batch_cu8(lcs_xcorr_plan* plan, const uint8_t* iq_host, uint32_t batch, lcs_cell* cells,
                                      uint32_t max_cells, uint32_t* n_cells);
+
+/* ---- many channels at once: frequency sweep and multi-channel tracker search -------------------------------------- */
+/* A sweep handle owns one search plan per channel (templates for every channel's k_factor built on the device in one
+ * launch) and the device buffers of the pipeline; all channels of a chunk go through ONE correlator launch.  n_cap is
+ * the capture-buffer length of every channel. */
+typedef struct lcs_sweep lcs_sweep;
+lcs_status lcs_sweep_create(lcs_ctx* ctx, uint32_t n_cap, lcs_sweep** sweep);
+void lcs_sweep_destroy(lcs_sweep* sweep);
+/* The per-centre-frequency loop of CellSearch (src/CellSearch.cpp:465-558) for n_ch capture buffers: iq_host is cu8
+ * [n_ch][n_cap][2]; fc_requested[n_ch]; fc_programmed[n_ch] or NULL (= fc_requested); one fs_programmed and one
+ * f_search_set for the whole sweep like the reference (:463-464 computes it from freq_start).  cells is
+ * [n_ch][max_cells], n_cells[n_ch]; apply lcs_dedup to the concatenation in channel order (CellSearch.cpp:560-562). */
+lcs_status lcs_sweep_search_cu8(lcs_sweep* sweep, const uint8_t* iq_host, uint32_t n_ch, const double* fc_requested,
+                                const double* fc_programmed, double fs_programmed, const double* f_search_set, uint32_t n_f,
+                                lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells);
+/* One searcher cycle (src/searcher_thread.cpp:95-232) for n_ch tracked channels: channel c is searched at the single
+ * offset frequency_offset[c]; tracked_n_id_cell is [n_ch][tracked_stride] with n_tracked[c] valid entries (both may be
+ * NULL); late[n_ch] or NULL; cells / frame_timing are [n_ch][max_cells].  Same results per channel as
+ * lcs_tracker_search_cu8. */
+lcs_status lcs_sweep_track_cu8(lcs_sweep* sweep, const uint8_t* iq_host, uint32_t n_ch, const double* frequency_offset,
+                               const double* fc_requested, const double* fc_programmed, double fs_programmed,
+                               const double* late, const int32_t* tracked_n_id_cell, const uint32_t* n_tracked,
+                               uint32_t tracked_stride, lcs_cell* cells, double* frame_timing, uint32_t max_cells,
+                               uint32_t* n_cells);
 
 /* ---- streaming (tracker) mode: producer framing + one searcher cycle ------------------------------------------ */
 /* Host-side framing of a continuous raw IQ byte stream into searcher capture buffers: the searcher part of

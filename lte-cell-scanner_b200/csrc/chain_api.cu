@@ -280,6 +280,41 @@ lcs_status lcs_cell_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t
                          fs_programmed, cells, max_cells, n_cells, peaks, n_peaks);
 }
 
+// kalibrate (src/LTE-Tracker.cpp:565-741): an initial full search whose only purpose is the oscillator's residual offset.
+// The frequency grid is centred on the offset implied by the current correction factor (:586-587); the strongest
+// surviving cell after dedup (:703-716) gives freq_superfine and the residual correction factor (:719-726).  The
+// reference loops until a cell is found (new data every iteration); here one buffer is examined and *n_cells = 0 reports
+// "nothing found, try the next buffer".
+lcs_status lcs_kalibrate_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n_cap, double fc_requested, double fc_programmed,
+                             double fs_programmed, double ppm, double correction, lcs_cell* best, double* correction_residual,
+                             uint32_t* n_cells) {
+  if (!ctx || !capbuf_cu8 || !best || !n_cells) return fail(ctx, LCS_ERR_ARG, "kalibrate_cu8: null argument");
+  LCS_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<double> f = f_search_set_for(fc_requested, ppm);                          // :586
+  for (double& v : f) v = (fc_requested * correction - fc_requested) + v;               // :587
+  LCS_CUDA(ctx, ctx->d_cu8.ensure((size_t)n_cap * 2 + 16));
+  LCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_cu8.p, capbuf_cu8, (size_t)n_cap * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
+  std::vector<lcs_cell> cells(64);
+  uint32_t found = 0;
+  lcs_status rc = cell_search_dev(ctx, ctx->d_cu8.p, LCS_IQ_CU8, n_cap, f.data(), (uint32_t)f.size(), fc_requested, fc_programmed,
+                                  fs_programmed, cells.data(), (uint32_t)cells.size(), &found, nullptr, nullptr);
+  if (rc != LCS_OK) return rc;
+  std::vector<lcs_cell> fin;
+  dedup(cells.data(), std::min<uint32_t>(found, (uint32_t)cells.size()), fin);           // :703-705
+  *n_cells = (uint32_t)fin.size();
+  lcs_cell_init(best);
+  if (fin.empty()) return LCS_OK;
+  double bp = -INFINITY;
+  for (const lcs_cell& c : fin)                                                         // :709-716
+    if (c.pss_pow > bp) { bp = c.pss_pow; *best = c; }
+  if (correction_residual) {
+    const double true_location = fc_requested;                                          // :720
+    const double crystal_freq_actual = fc_programmed - best->freq_superfine;            // :722
+    *correction_residual = (true_location / fc_requested * fc_programmed) / crystal_freq_actual;   // :724
+  }
+  return LCS_OK;
+}
+
 // One cycle of the tracker's searcher thread (src/searcher_thread.cpp:95-232) on a capture buffer delivered by the framer.
 lcs_status lcs_tracker_search_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n_cap, double frequency_offset,
                                   double fc_requested, double fc_programmed, double fs_programmed, double late,

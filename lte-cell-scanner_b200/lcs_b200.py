@@ -75,6 +75,8 @@ def lib():
         _lib.lcs_xcorr_plan_timing_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.lcs_xcorr_plan_timing_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.lcs_framer_destroy.argtypes = [C.c_void_p]
+        _lib.lcs_sweep_destroy.argtypes = [C.c_void_p]
+        _lib.lcs_sweep_destroy.restype = None
         _lib.lcs_framer_destroy.restype = None
         _lib.lcs_framer_request.argtypes = [C.c_void_p]
         _lib.lcs_framer_request.restype = None
@@ -268,6 +270,15 @@ class Context:
                                           C.c_uint32(max_cells), C.byref(n)), self._h)
         return [(_copy(cells[i]), ft[i]) for i in range(min(n.value, max_cells))]
 
+    def kalibrate_cu8(self, capbuf_cu8, fc_requested, fc_programmed, fs_programmed, ppm, correction=1.0):
+        """LTE-Tracker.cpp:565-741.  Returns (best Cell or None, correction_residual, number of cells found)."""
+        cb = np.ascontiguousarray(capbuf_cu8, np.uint8)
+        best = Cell(); res = C.c_double(0); n = C.c_uint32(0)
+        _chk(lib().lcs_kalibrate_cu8(self._h, _p(cb), C.c_uint32(cb.size // 2), C.c_double(fc_requested), C.c_double(fc_programmed),
+                                     C.c_double(fs_programmed), C.c_double(ppm), C.c_double(correction), C.byref(best), C.byref(res),
+                                     C.byref(n)), self._h)
+        return (best if n.value else None), res.value, n.value
+
     def plan(self, n_cap, f_set, ds_comb_arm, fc_requested, fc_programmed, fs_programmed, max_batch=1,
              kernel=KERNEL_AUTO):
         return XcorrPlan(self, n_cap, f_set, ds_comb_arm, fc_requested, fc_programmed, fs_programmed, max_batch, kernel)
@@ -358,6 +369,71 @@ class XcorrPlan:
         _chk(lib().lcs_cell_search_batch_cu8(self._h, C.c_void_p(host_ptr), C.c_uint32(batch), cells, C.c_uint32(max_cells), n),
              self.ctx._h)
         return [[_copy(cells[b * max_cells + k]) for k in range(min(n[b], max_cells))] for b in range(batch)]
+
+
+class Sweep:
+    """lcs_sweep: many channels (centre frequencies / tracked channels) through one correlator launch per chunk."""
+
+    def __init__(self, ctx, n_cap=153600):
+        self.ctx = ctx
+        self.n_cap = int(n_cap)
+        self._h = C.c_void_p()
+        _chk(lib().lcs_sweep_create(ctx._h, C.c_uint32(n_cap), C.byref(self._h)), ctx._h)
+
+    def close(self):
+        if self._h:
+            lib().lcs_sweep_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search_cu8(self, iq_cu8, fc_requested, f_set, fs_programmed=1.92e6, fc_programmed=None, max_cells=8, host_ptr=None):
+        """CellSearch.cpp:465-558 for all channels.  iq_cu8: uint8 [n_ch][n_cap][2] (or host_ptr).  Returns a list
+        (per channel) of lists of Cells."""
+        fc = np.ascontiguousarray(fc_requested, np.float64)
+        n_ch = fc.size
+        fcp = None if fc_programmed is None else np.ascontiguousarray(fc_programmed, np.float64)
+        f = np.ascontiguousarray(f_set, np.float64)
+        if host_ptr is None:
+            iq_cu8 = np.ascontiguousarray(iq_cu8, np.uint8)
+            host_ptr = iq_cu8.ctypes.data
+        cells = (Cell * (n_ch * max_cells))()
+        n = (C.c_uint32 * n_ch)()
+        _chk(lib().lcs_sweep_search_cu8(self._h, C.c_void_p(host_ptr), C.c_uint32(n_ch), _p(fc), _p(fcp), C.c_double(fs_programmed),
+                                        _p(f), C.c_uint32(f.size), cells, C.c_uint32(max_cells), n), self.ctx._h)
+        return [[_copy(cells[b * max_cells + k]) for k in range(min(n[b], max_cells))] for b in range(n_ch)]
+
+    def track_cu8(self, iq_cu8, frequency_offset, fc_requested, fs_programmed=1.92e6, fc_programmed=None, late=None, tracked=None,
+                  max_cells=8, host_ptr=None):
+        """searcher_thread.cpp:95-232 for all channels.  tracked: list (per channel) of lists of n_id_cell.  Returns a
+        list (per channel) of [(Cell, frame_timing), ...]."""
+        fo = np.ascontiguousarray(frequency_offset, np.float64)
+        fc = np.ascontiguousarray(fc_requested, np.float64)
+        n_ch = fc.size
+        fcp = None if fc_programmed is None else np.ascontiguousarray(fc_programmed, np.float64)
+        lt = None if late is None else np.ascontiguousarray(late, np.float64)
+        tr = nt = None
+        stride = 0
+        if tracked is not None:
+            stride = max(1, max(len(t) for t in tracked))
+            tr = np.full((n_ch, stride), -1, np.int32)
+            nt = np.zeros(n_ch, np.uint32)
+            for c, t in enumerate(tracked):
+                tr[c, :len(t)] = t
+                nt[c] = len(t)
+        if host_ptr is None:
+            iq_cu8 = np.ascontiguousarray(iq_cu8, np.uint8)
+            host_ptr = iq_cu8.ctypes.data
+        cells = (Cell * (n_ch * max_cells))()
+        ft = (C.c_double * (n_ch * max_cells))()
+        n = (C.c_uint32 * n_ch)()
+        _chk(lib().lcs_sweep_track_cu8(self._h, C.c_void_p(host_ptr), C.c_uint32(n_ch), _p(fo), _p(fc), _p(fcp), C.c_double(fs_programmed),
+                                       _p(lt), _p(tr), _p(nt), C.c_uint32(stride), cells, ft, C.c_uint32(max_cells), n), self.ctx._h)
+        return [[(_copy(cells[b * max_cells + k]), ft[b * max_cells + k]) for k in range(min(n[b], max_cells))] for b in range(n_ch)]
 
 
 class Framer:

@@ -43,21 +43,17 @@ def array_to_cells(a, new_cell):
     return out
 
 
-def sweep(channels, search_fn, new_cell, dedup_fn, dist=None, device=None, max_cells_per_rank=256):
-    """channels: list of (channel_index, fc_requested, capbuf).  search_fn(fc, capbuf) -> list of cells.
-    Returns the deduplicated list on rank 0 (None elsewhere).  `dist` is torch.distributed (initialised)
-    or None for a single process."""
-    rank = dist.get_rank() if dist is not None else 0
-    world = dist.get_world_size() if dist is not None else 1
-    mine = []           # (channel index, cells) in channel order
-    for pos in shard(len(channels), rank, world):
-        idx, fc, cap = channels[pos]
-        mine.append((idx, search_fn(fc, cap)))
+def gather_dedup(mine, new_cell, dedup_fn, dist=None, device=None, max_cells_per_rank=256):
+    """mine: [(channel index, [cells])] of this rank.  One all_gather of the fixed-size cell records (NCCL over NVLink on
+    GPUs, gloo on CPU), then the reference's cross-frequency dedup (CellSearch.cpp:285-319) on rank 0 in channel order.
+    Returns the final list on rank 0, None elsewhere."""
     flat = [c for _, cs in mine for c in cs]
     order = [idx for idx, cs in mine for _ in cs]
     if dist is None:
-        return dedup_fn(flat)
+        tagged = sorted(zip(order, range(len(flat))), key=lambda x: x[0])
+        return dedup_fn([flat[i] for _, i in tagged])
     import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
     arr = cells_to_array(flat, max_cells_per_rank)
     tag = np.full((max_cells_per_rank + 1, 1), -1.0)
     tag[1:1 + len(order), 0] = order[:max_cells_per_rank]
@@ -77,3 +73,27 @@ def sweep(channels, search_fn, new_cell, dedup_fn, dist=None, device=None, max_c
     # dedup depends on the order in which equal-power candidates are met
     tagged.sort(key=lambda x: x[0])
     return dedup_fn([c for _, c in tagged])
+
+
+def sweep(channels, search_fn, new_cell, dedup_fn, dist=None, device=None, max_cells_per_rank=256):
+    """channels: list of (channel_index, fc_requested, capbuf).  search_fn(fc, capbuf) -> list of cells (one channel at a
+    time).  Returns the deduplicated list on rank 0 (None elsewhere).  `dist` is torch.distributed (initialised) or None
+    for a single process."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    mine = []           # (channel index, cells) in channel order
+    for pos in shard(len(channels), rank, world):
+        idx, fc, cap = channels[pos]
+        mine.append((idx, search_fn(fc, cap)))
+    return gather_dedup(mine, new_cell, dedup_fn, dist, device, max_cells_per_rank)
+
+
+def sweep_batched(fc_all, iq_mine, batch_search_fn, new_cell, dedup_fn, dist=None, device=None, max_cells_per_rank=256):
+    """All channels of this rank in one call.  fc_all: centre frequencies of ALL channels (every rank); iq_mine: this
+    rank's capture buffers in the order of shard(len(fc_all), rank, world); batch_search_fn(iq, fcs) -> list (per channel)
+    of lists of cells (lcs_sweep_search_cu8)."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    idx = shard(len(fc_all), rank, world)
+    res = batch_search_fn(iq_mine, [fc_all[i] for i in idx]) if idx else []
+    return gather_dedup(list(zip(idx, res)), new_cell, dedup_fn, dist, device, max_cells_per_rank)

@@ -464,3 +464,98 @@ def test_tracker_search_vs_oracle(ctx, lcs, oracle, capbuf0000):
         assert abs(a.frame_start - b.frame_start) < 1e-9
         assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6
         assert abs(ft - (b.frame_start * (30720000.0 / 16) / (fs * k) + 0.25)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# many channels at once (BASELINE configs 4 and 5): one plan per channel, one correlator launch per chunk
+# ---------------------------------------------------------------------------------------------
+def test_sweep_search_vs_oracle(ctx, lcs, oracle, capbuf0000):
+    """lcs_sweep_search_cu8 = the per-centre-frequency loop of CellSearch.cpp:465-558.  The real capture is presented at
+    three different centre frequencies (different k_factor => different templates and fold offsets per channel) between
+    noise channels, more channels than one chunk; every channel is compared with the oracle's chain for that channel."""
+    f = lcs.f_search_set(739e6, 120.0)                       # one f_search_set for the sweep (CellSearch.cpp:463-464)
+    real, noise = capbuf0000["cu8"], synth_cu8(0xBEEF)
+    fcs = 739e6 + 100e3 * np.arange(70)
+    is_real = {0: 0, 33: 1, 69: 2}
+    iq = np.stack([real if i in is_real else noise for i in range(fcs.size)])
+    sw = lcs.Sweep(ctx, real.shape[0])
+    got = sw.search_cu8(iq, fcs, f)
+    o_noise, _ = oracle.cell_search_one(cu8_to_c128(noise), f, 739e6, 739e6, 1.92e6)
+    assert o_noise == []
+    for i, fc in enumerate(fcs):
+        if i not in is_real:
+            assert got[i] == [], i
+            continue
+        o_cells, _ = oracle.cell_search_one(capbuf0000["capbuf"], f, fc, fc, 1.92e6)
+        assert [c.n_id_cell() for c in got[i]] == [c.n_id_cell() for c in o_cells] and len(o_cells) >= 1
+        for a, b in zip(got[i], o_cells):
+            for k in ("n_id_1", "n_id_2", "cp_type", "ind", "n_ports", "n_rb_dl", "phich_duration", "phich_resource", "sfn"):
+                assert getattr(a, k) == getattr(b, k), (i, k)
+            assert a.fc_requested == fc and a.freq == b.freq
+            assert abs(a.pss_pow - b.pss_pow) < REL * b.pss_pow * 10
+            assert abs(a.frame_start - b.frame_start) < 1e-9
+            assert abs(a.freq_fine - b.freq_fine) < 1e-6 and abs(a.freq_superfine - b.freq_superfine) < 1e-6
+    # a second sweep through the same handle with other channels (plans are rebuilt)
+    got2 = sw.search_cu8(iq[:3], fcs[:3] + 5e6, f)
+    assert len(got2[0]) >= 1 and got2[1] == [] and got2[2] == []
+    sw.close()
+
+
+def test_sweep_track_matches_tracker_search(ctx, lcs, capbuf0000):
+    """lcs_sweep_track_cu8 (all channels in one launch, per-channel offset) == lcs_tracker_search_cu8 per channel."""
+    fc = capbuf0000["fc"]
+    real, noise = capbuf0000["cu8"], synth_cu8(0xFEED)
+    offs = [35228.0, 35000.0, -1200.0, 35228.0, 36000.0]
+    fcs = [fc, fc, fc + 1e6, fc + 2e6, fc]
+    bufs = [real, real, noise, real, real]
+    late = [0.25, -0.5, 0.0, 1.5, 0.0]
+    tracked = [[], [], [], [277], [271, 5]]
+    sw = lcs.Sweep(ctx, real.shape[0])
+    got = sw.track_cu8(np.stack(bufs), offs, fcs, late=late, tracked=tracked)
+    for c in range(len(bufs)):
+        ref = ctx.tracker_search_cu8(bufs[c], offs[c], fcs[c], fcs[c], 1.92e6, late[c], tracked=tracked[c])
+        assert len(got[c]) == len(ref), c
+        for (a, fa), (b, fb) in zip(got[c], ref):
+            assert a.as_dict() == b.as_dict() and fa == fb
+    assert [c.n_id_cell() for c, _ in got[0]] == [277, 271] and got[2] == []
+    assert 277 not in [c.n_id_cell() for c, _ in got[3]]
+    sw.close()
+
+
+def test_kalibrate_vs_oracle(ctx, lcs, oracle, capbuf0000):
+    """kalibrate (LTE-Tracker.cpp:565-741): offset-centred grid, chain, dedup, strongest cell, residual correction factor -
+    against the same steps done with the oracle.  capbuf_0000: cell 277, freq_superfine 35 228.46 Hz."""
+    fc = capbuf0000["fc"]; fs = 1.92e6
+    for correction in (1.0, 1.00004):
+        f = (fc * correction - fc) + oracle.f_search_set(fc, 120.0)                       # :586-587
+        o_cells, _ = oracle.cell_search_one(capbuf0000["capbuf"], f, fc, fc, fs)
+        o_fin = oracle.dedup(o_cells)
+        o_best = max(o_fin, key=lambda c: c.pss_pow)
+        best, resid, n = ctx.kalibrate_cu8(capbuf0000["cu8"], fc, fc, fs, 120.0, correction)
+        assert n == len(o_fin) and best is not None
+        assert best.n_id_cell() == o_best.n_id_cell() == 277
+        assert abs(best.freq_superfine - o_best.freq_superfine) < 1e-6
+        assert abs(resid - fc / (fc - o_best.freq_superfine)) < 1e-15
+    assert abs(best.freq_superfine - 35228.46) < 0.5
+    none, _, n0 = ctx.kalibrate_cu8(synth_cu8(1), fc, fc, fs, 120.0)
+    assert none is None and n0 == 0
+
+
+def test_stream_search_cli_kalibrate(ctx, tmp_path, capbuf0000):
+    """StreamSearch_b200 = LTE-Tracker's start-up on a recorded stream: kalibrate on the first buffer (LTE-Tracker.cpp:795-798),
+    then producer framing + searcher cycles at the calibrated offset."""
+    import os
+    import re
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    host = os.path.join(root, "lte-cell-scanner_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    real = capbuf0000["cu8"]
+    stream = np.concatenate([real, real, real[:40000]])
+    stream.tofile(str(tmp_path / "stream.bin"))
+    out = subprocess.run([os.path.join(host, "StreamSearch_b200"), "-f", "739000000", "-n", "1", str(tmp_path / "stream.bin")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    m = re.search(r"Residual frequency offset: ([0-9.]+) Hz", out.stdout)
+    assert m and abs(float(m.group(1)) - 35228.46) < 0.5
+    assert re.search(r"new cell 277 ", out.stdout)

@@ -36,8 +36,13 @@ WORKER = textwrap.dedent('''
         dist.init_process_group("gloo")
         d = dist
     res = sweep.sweep(chans, fake_search, L.new_cell, L.dedup, dist=d)
+    # the batched variant (all channels of a rank in one call, lcs_sweep_search_cu8) must give the same final list
+    fcs = [c[1] for c in chans]
+    res2 = sweep.sweep_batched(fcs, None, lambda iq, f: [fake_search(x, None) for x in f], L.new_cell, L.dedup, dist=d)
     if res is not None:
-        print("RESULT " + json.dumps([[c.n_id_cell(), c.fc_requested, c.pss_pow, c.ind] for c in res]))
+        key = lambda r: [[c.n_id_cell(), c.fc_requested, c.pss_pow, c.ind] for c in r]
+        assert key(res) == key(res2)
+        print("RESULT " + json.dumps(key(res)))
     if world > 1:
         dist.destroy_process_group()
 ''')
