@@ -102,8 +102,7 @@ static lcs_status peaks_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n
   LCS_CUDA(ctx, ctx->d_pow.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_frq.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_spi.ensure(LCS_N_FOLD));
-  LCS_CUDA(ctx, ctx->d_spp.ensure((size_t)p->ps.geom.n_comb_sp * LCS_N_FOLD));
-  rc = plan_run_device(p, d_cap, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p, nullptr, ctx->d_spp.p, st);
+  rc = plan_run_device(p, d_cap, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p, nullptr, st);
   if (rc != LCS_OK) return rc;
   std::vector<double> pw(3 * LCS_N_FOLD), spi(LCS_N_FOLD), z(LCS_N_FOLD);
   std::vector<int32_t> fq(3 * LCS_N_FOLD);

@@ -334,8 +334,18 @@ void pbch_ratematch_positions(int n_e, std::vector<int>& pos) {
 
 // exact maximum-likelihood tail-biting Viterbi: best path over all 64 (start==end) states.
 // llr > 0 means bit 0 (lte_lib.cpp:465-468, 535-537).
+// The 64 constrained decodes (one per start state) are independent: their path metrics are kept side by side,
+// m[state][start], so that the add-compare-select of one trellis branch is a 64-wide element-wise operation the compiler
+// vectorises (AVX2 / AVX-512 clones are selected at load time).  Every metric is the same sequence of double additions
+// and every decision the same strict comparison as in a start-state-at-a-time decoder, so the decoded bits are identical.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDACC__)
+#define LCS_SIMD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define LCS_SIMD_CLONES
+#endif
+LCS_SIMD_CLONES
 void viterbi_tailbite(const double* llr /*[3][40]*/, uint8_t* bits /*[40]*/) {
-  const int L = 40, S = 64;
+  constexpr int L = 40, S = 64;
   int out[64][2];
   for (int s = 0; s < S; s++)
     for (int b = 0; b < 2; b++) {
@@ -349,31 +359,38 @@ void viterbi_tailbite(const double* llr /*[3][40]*/, uint8_t* bits /*[40]*/) {
       for (int j = 0; j < 3; j++) g += ((o >> j) & 1) ? -llr[j * L + l] : llr[j * L + l];
       gain[l][o] = g;
     }
+  alignas(64) static thread_local double ma[64][64], mb[64][64];
+  alignas(64) static thread_local uint8_t dec[40][64][64];   // [step][state][start]: 1 = the odd predecessor won
+  double (*m)[64] = ma, (*m2)[64] = mb;
+  for (int s = 0; s < S; s++)
+    for (int s0 = 0; s0 < S; s0++) m[s][s0] = s == s0 ? 0.0 : -INFINITY;
+  for (int l = 0; l < L; l++) {
+    for (int ns = 0; ns < S; ns++) {
+      const int b = ns >> 5;                       // input bit that leads into ns
+      const int p0 = (ns << 1) & 63, p1 = p0 | 1;  // predecessors: (reg>>1)==ns
+      const double g0 = gain[l][out[p0][b]], g1 = gain[l][out[p1][b]];
+      const double* __restrict__ a0 = m[p0];
+      const double* __restrict__ a1 = m[p1];
+      double* __restrict__ o = m2[ns];
+      uint8_t* __restrict__ d = dec[l][ns];
+      for (int s0 = 0; s0 < S; s0++) {
+        const double c0 = a0[s0] + g0, c1 = a1[s0] + g1;
+        const bool hi = c1 > c0;
+        o[s0] = hi ? c1 : c0;
+        d[s0] = (uint8_t)hi;
+      }
+    }
+    std::swap(m, m2);
+  }
   double best = -INFINITY;
-  for (int s0 = 0; s0 < S; s0++) {
-    double m[64], m2[64];
-    uint64_t from_hi[40];  // decision bit per state: which of the two predecessors won
-    for (int s = 0; s < S; s++) m[s] = -INFINITY;
-    m[s0] = 0;
-    for (int l = 0; l < L; l++) {
-      uint64_t dec = 0;
-      for (int ns = 0; ns < S; ns++) {
-        const int b = ns >> 5;                 // input bit that leads into ns
-        const int p0 = (ns << 1) & 63, p1 = p0 | 1;  // predecessors: (reg>>1)==ns
-        const double c0 = m[p0] + gain[l][out[p0][b]], c1 = m[p1] + gain[l][out[p1][b]];
-        if (c1 > c0) { m2[ns] = c1; dec |= 1ull << ns; } else m2[ns] = c0;
-      }
-      from_hi[l] = dec;
-      std::memcpy(m, m2, sizeof(m));
-    }
-    if (m[s0] > best) {
-      best = m[s0];
-      int s = s0;
-      for (int l = L - 1; l >= 0; l--) {
-        bits[l] = (uint8_t)(s >> 5);
-        s = ((s << 1) & 63) | (int)((from_hi[l] >> s) & 1);
-      }
-    }
+  int best_s0 = -1;
+  for (int s0 = 0; s0 < S; s0++)
+    if (m[s0][s0] > best) { best = m[s0][s0]; best_s0 = s0; }
+  if (best_s0 < 0) best_s0 = 0;     // all metrics NaN / -inf: the start-state-at-a-time decoder would leave `bits` untouched
+  int s = best_s0;
+  for (int l = L - 1; l >= 0; l--) {
+    bits[l] = (uint8_t)(s >> 5);
+    s = ((s << 1) & 63) | (int)dec[l][s][best_s0];
   }
 }
 

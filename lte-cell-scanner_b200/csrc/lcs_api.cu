@@ -44,7 +44,6 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
   cudaStream_t st = ctx->streams[0];
   lcs_status rc = planset_build(ctx, p->ps, n_cap, arm, cfg, true, st);
   if (rc != LCS_OK) return rc;
-  LCS_CUDA(ctx, p->d_sp_partial.alloc((size_t)max_batch * p->ps.geom.n_comb_sp * LCS_N_FOLD));
   // the plan is used from arbitrary streams afterwards: finish the build here and read the builder's diagnostics
   int flag = 0;
   LCS_CUDA(ctx, cudaMemcpyAsync(&flag, p->ps.d_flag.p, 4, cudaMemcpyDeviceToHost, st));
@@ -55,11 +54,11 @@ static lcs_status build_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_searc
 }
 
 static lcs_status run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single,
-                             double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial, cudaStream_t st) {
+                             double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st) {
   lcs_ctx* ctx = p->ctx;
   if (batch == 0 || batch > p->max_batch) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: batch exceeds plan max_batch");
   if (!p->timing)
-    return planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st);
+    return planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, st);
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   if (p->ev_pool.empty()) {
     LCS_CUDA(ctx, cudaEventCreate(&ev.first));
@@ -68,15 +67,15 @@ static lcs_status run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format,
     ev = p->ev_pool.back();
     p->ev_pool.pop_back();
   }
-  lcs_status rc = planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st, &ev);
+  lcs_status rc = planset_run(p->ps, p->kernel, d_iq, iq_format, batch, nullptr, d_single, d_pow, d_frq, d_spi, d_inc, st, &ev);
   if (rc != LCS_OK) { p->ev_pool.push_back(ev); return rc; }     // nothing usable was recorded
   p->ev_used.push_back(ev);
   return LCS_OK;
 }
 
 lcs_status plan_run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single, double* d_pow,
-                           int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial, cudaStream_t st) {
-  return run_device(p, d_iq, iq_format, batch, d_single, d_pow, d_frq, d_spi, d_inc, d_sp_partial, st);
+                           int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st) {
+  return run_device(p, d_iq, iq_format, batch, d_single, d_pow, d_frq, d_spi, d_inc, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,7 +234,7 @@ lcs_status lcs_xcorr_pss_device(lcs_xcorr_plan* plan, const void* d_iq, int iq_f
                                 float* d_incoherent_planar, void* stream) {
   if (!plan) return fail(nullptr, LCS_ERR_ARG, "xcorr_pss_device: null plan");
   return run_device(plan, d_iq, iq_format, batch, d_single_planar, d_pow, d_frq, d_sp_incoherent, d_incoherent_planar,
-                    plan->d_sp_partial.p, (cudaStream_t)stream);
+                    (cudaStream_t)stream);
 }
 
 // Host-buffer batched call: chunks of the batch alternate between the context's two streams so
@@ -260,7 +259,6 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
     LCS_CUDA(ctx, p->hb[s].pow.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, p->hb[s].frq.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, p->hb[s].spi.ensure((size_t)chunk * LCS_N_FOLD));
-    LCS_CUDA(ctx, p->hb[s].sp_partial.ensure((size_t)chunk * g.n_comb_sp * LCS_N_FOLD));
   }
   int s = 0;
   for (uint32_t b0 = 0; b0 < batch; b0 += chunk, s ^= 1) {
@@ -269,7 +267,7 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
     auto& hb = p->hb[s];
     LCS_CUDA(ctx, cudaMemcpyAsync(hb.iq.p, (const char*)h_iq + (size_t)b0 * g.n_cap * samp_bytes,
                                   (size_t)nb * g.n_cap * samp_bytes, cudaMemcpyHostToDevice, st));
-    lcs_status rc = run_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, hb.sp_partial.p, st);
+    lcs_status rc = run_device(p, hb.iq.p, iq_format, nb, hb.single.p, hb.pow.p, hb.frq.p, hb.spi.p, nullptr, st);
     if (rc != LCS_OK) return rc;
     if (h_single)
       LCS_CUDA(ctx, cudaMemcpyAsync(h_single + (size_t)b0 * n_single, hb.single.p, (size_t)nb * n_single * 4, cudaMemcpyDeviceToHost, st));
@@ -303,7 +301,6 @@ lcs_status lcs_xcorr_pss(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap, con
   LCS_CUDA(ctx, ctx->d_pow.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_frq.ensure(3 * LCS_N_FOLD));
   LCS_CUDA(ctx, ctx->d_spi.ensure(LCS_N_FOLD));
-  LCS_CUDA(ctx, ctx->d_spp.ensure((size_t)g.n_comb_sp * LCS_N_FOLD));
   LCS_CUDA(ctx, cudaMemcpyAsync(ctx->d_capbuf.p, capbuf, (size_t)n_cap * 16, cudaMemcpyHostToDevice, st));
   // 8-bit exact input (an rtl-sdr capture, capbuf.cpp:172-175) goes to the tensor-core correlator
   const void* d_in = ctx->d_capbuf.p;
@@ -320,7 +317,7 @@ lcs_status lcs_xcorr_pss(lcs_ctx* ctx, const double* capbuf, uint32_t n_cap, con
     if (!inexact) { d_in = ctx->d_cu8.p; fmt = LCS_IQ_CU8; }
   }
   rc = run_device(p, d_in, fmt, 1, ctx->d_single.p, ctx->d_pow.p, ctx->d_frq.p, ctx->d_spi.p,
-                  incoherent ? ctx->d_inc.p : nullptr, ctx->d_spp.p, st);
+                  incoherent ? ctx->d_inc.p : nullptr, st);
   if (rc != LCS_OK) return rc;
   // reference layouts: vf3d [t][idx][f]; mat(3,9600) column-major
   ctx->launches += launch_planar_to_ref(g, ctx->d_single.p, ctx->d_ref.p, st);

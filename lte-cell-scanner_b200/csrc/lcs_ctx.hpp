@@ -100,7 +100,7 @@ struct lcs_ctx {
   // scratch of the drop-in host calls
   lcs::DevBuf<double> d_capbuf;                // c128 capture buffer (2 doubles / sample)
   lcs::DevBuf<float> d_single, d_ref, d_inc;
-  lcs::DevBuf<double> d_pow, d_spi, d_spp;
+  lcs::DevBuf<double> d_pow, d_spi;
   lcs::DevBuf<int32_t> d_frq;
   lcs::DevBuf<double> d_work;                  // sss / tfg kernels
   lcs::DevBuf<unsigned char> d_cu8;
@@ -113,7 +113,6 @@ struct lcs_xcorr_plan {
   lcs::PlanSet ps;
   uint32_t max_batch = 1;
   int kernel = LCS_KERNEL_AUTO;
-  lcs::DevBuf<double> d_sp_partial;            // scratch of lcs_xcorr_pss_device (one stream at a time, see lcs_b200.h)
   // kernel timing hook
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_used;
@@ -121,7 +120,7 @@ struct lcs_xcorr_plan {
   struct HostBatchBufs {
     lcs::DevBuf<unsigned char> iq;
     lcs::DevBuf<float> single;
-    lcs::DevBuf<double> pow, spi, sp_partial;
+    lcs::DevBuf<double> pow, spi;
     lcs::DevBuf<int32_t> frq;
     // device peak search (search_batch.cu)
     lcs::DevBuf<double> work;
@@ -150,11 +149,11 @@ lcs_status planset_build(lcs_ctx* ctx, PlanSet& ps, uint32_t n_cap, uint8_t arm,
 // Which kernel AUTO resolves to for this set and input format.
 int planset_resolve_kernel(const PlanSet& ps, int kernel, int iq_format);
 // xcorr_pss for `batch` device-resident capture buffers: correlator + sp_est + delay spread / argmax.  d_buf_plan
-// (device, [batch]) names the plan of every buffer (NULL: plan 0).  d_sp_partial: [batch][n_comb_sp][9600] scratch.
+// (device, [batch]) names the plan of every buffer (NULL: plan 0).
 // ev: optional event pair recorded around the correlator kernel.
 lcs_status planset_run(PlanSet& ps, int kernel, const void* d_iq, int iq_format, uint32_t batch, const uint32_t* d_buf_plan,
-                       float* d_single, double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial,
-                       cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr);
+                       float* d_single, double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st,
+                       const std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr);
 
 lcs_status get_cached_plan(lcs_ctx* ctx, uint32_t n_cap, const double* f_search_set, uint32_t n_f, uint8_t arm,
                            double fc_req, double fc_prog, double fs_prog, lcs_xcorr_plan** out);
@@ -169,6 +168,6 @@ int launch_xcorr_fold_tc(PlanSet& ps, const void* d_iq_cu8, uint32_t batch, cons
 void tc_prof_dump();
 // ---- lcs_api.cu ----
 lcs_status plan_run_device(lcs_xcorr_plan* p, const void* d_iq, int iq_format, uint32_t batch, float* d_single, double* d_pow,
-                           int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial, cudaStream_t st);
+                           int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st);
 
 }  // namespace lcs

@@ -42,11 +42,10 @@ struct PlanView {
 int launch_xcorr_fold_fp32(const XcorrGeom& g, const PlanView& pv, const void* d_iq, int iq_format, uint32_t batch,
                            const float4* d_w01, const float2* d_w2, const int* d_soff, const int* d_smin,
                            float* d_single_planar, cudaStream_t st);
-int launch_sp_partial(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_partial,
-                      cudaStream_t st);
-int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, const float* d_single_planar,
-                    const double* d_sp_partial, double* d_pow, int32_t* d_frq, double* d_sp_incoherent,
-                    float* d_incoherent_planar, cudaStream_t st);
+int launch_sp_fold(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_incoherent,
+                   cudaStream_t st);
+int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, const float* d_single_planar, double* d_pow,
+                    int32_t* d_frq, float* d_incoherent_planar, cudaStream_t st);
 // ref-layout conversions for the drop-in host call
 int launch_planar_to_ref(const XcorrGeom& g, const float* d_planar, float* d_ref, cudaStream_t st);
 int launch_xc_debug(const XcorrGeom& g, const void* d_iq, int iq_format, const float4* d_w01, const float2* d_w2,

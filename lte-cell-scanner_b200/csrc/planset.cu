@@ -272,10 +272,10 @@ int planset_resolve_kernel(const PlanSet& ps, int kernel, int iq_format) {
 }
 
 lcs_status planset_run(PlanSet& ps, int kernel, const void* d_iq, int iq_format, uint32_t batch, const uint32_t* d_buf_plan,
-                       float* d_single, double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, double* d_sp_partial,
-                       cudaStream_t st, const std::pair<cudaEvent_t, cudaEvent_t>* ev) {
+                       float* d_single, double* d_pow, int32_t* d_frq, double* d_spi, float* d_inc, cudaStream_t st,
+                       const std::pair<cudaEvent_t, cudaEvent_t>* ev) {
   lcs_ctx* ctx = ps.ctx;
-  if (!d_iq || !d_single || !d_pow || !d_frq || !d_spi || !d_sp_partial) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: null pointer");
+  if (!d_iq || !d_single || !d_pow || !d_frq || !d_spi) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: null pointer");
   if (batch == 0) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: empty batch");
   if (iq_format != LCS_IQ_CF32 && iq_format != LCS_IQ_CU8 && iq_format != LCS_IQ_C128)
     return fail(ctx, LCS_ERR_ARG, "xcorr_pss_device: bad iq_format");
@@ -297,8 +297,8 @@ lcs_status planset_run(PlanSet& ps, int kernel, const void* d_iq, int iq_format,
     ctx->launches += launch_xcorr_fold_fp32(ps.geom, pv, d_iq, iq_format, batch, ps.d_w01.p, ps.d_w2.p, ps.d_soff.p, ps.d_smin.p,
                                             d_single, st);
   if (ev) LCS_CUDA(ctx, cudaEventRecord(ev->second, st));
-  ctx->launches += launch_sp_partial(ps.geom, d_iq, iq_format, batch, d_sp_partial, st);
-  ctx->launches += launch_epilogue(ps.geom, pv, batch, d_single, d_sp_partial, d_pow, d_frq, d_spi, d_inc, st);
+  ctx->launches += launch_sp_fold(ps.geom, d_iq, iq_format, batch, d_spi, st);
+  ctx->launches += launch_epilogue(ps.geom, pv, batch, d_single, d_pow, d_frq, d_inc, st);
   LCS_CUDA(ctx, cudaGetLastError());
   return LCS_OK;
 }

@@ -155,7 +155,6 @@ static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr
     LCS_CUDA(ctx, hb.pow.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.frq.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.spi.ensure((size_t)chunk * LCS_N_FOLD));
-    LCS_CUDA(ctx, hb.sp_partial.ensure((size_t)chunk * g.n_comb_sp * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.work.ensure((size_t)chunk * 3 * LCS_N_FOLD));
     LCS_CUDA(ctx, hb.peaks.ensure((size_t)chunk * SEARCH_MAX_PEAKS * sizeof(DevPeak)));
     LCS_CUDA(ctx, hb.npeaks.ensure(chunk));
@@ -173,7 +172,7 @@ static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr
     LCS_CUDA(ctx, cudaMemcpyAsync(hb.iq.p, (const char*)h_iq + (size_t)b0 * g.n_cap * samp_bytes, (size_t)nb * g.n_cap * samp_bytes,
                                   cudaMemcpyHostToDevice, st));
     lcs_status rc = planset_run(ps, kernel, hb.iq.p, iq_format, nb, d_buf_plan ? d_buf_plan + b0 : nullptr, hb.single.p, hb.pow.p,
-                                hb.frq.p, hb.spi.p, nullptr, hb.sp_partial.p, st);
+                                hb.frq.p, hb.spi.p, nullptr, st);
     if (rc != LCS_OK) return rc;
     rc = launch_peak_search(ctx, g, nb, hb.pow.p, hb.frq.p, hb.spi.p, hb.single.p, hb.work.p, reinterpret_cast<DevPeak*>(hb.peaks.p),
                             hb.npeaks.p, SEARCH_MAX_PEAKS, st);

@@ -216,14 +216,13 @@ int launch_xcorr_fold_fp32(const XcorrGeom& g, const PlanView& pv, const void* d
 }
 
 // ------------------------------------------------------------------------------------------
-// sp_est  (searcher.cpp:185-221): sp[t] = mean_{j<274} |x[t+j]|^2 for t < n_comb_sp*9600.
-// One thread = 8 consecutive t of one half frame: a 274-term sum, then 7 slides.  FP64.
-// Output sp_partial[b][m][i] (i<9600); the fold over m happens in the epilogue.
+// sp_est  (searcher.cpp:185-221): sp[t] = mean_{j<274} |x[t+j]|^2 for t < n_comb_sp*9600, folded by 9600, averaged and
+// shifted right by 137 (:213-220).  FP64 like the reference.
+// One block = 1024 consecutive fold positions: for every half frame m the 1024+273 sample powers are summed with a
+// block-wide FP64 prefix scan, sp[t] = (S[t+274]-S[t])/274, and the fold  sp[0][i] + sp[1][i] + ...  is accumulated in
+// registers in the reference's order - only sp_incoherent is written.  For 8-bit IQ every term is a multiple of 2^-14
+// and every partial sum (< 2^7) is exact in double, so sp[t] is the exactly rounded quotient.
 // ------------------------------------------------------------------------------------------
-// One block = 1024 consecutive t of one half frame: the 1024+273 sample powers are summed with a
-// block-wide FP64 prefix scan, then sp[t] = (S[t+274]-S[t])/274.  For 8-bit IQ every term is a
-// multiple of 2^-14 and every partial sum (< 2^7) is exact in double, so the result is the exactly
-// rounded quotient.
 constexpr int SP_TILE = 1024;
 constexpr int SP_THREADS = 256;
 constexpr int SP_ITEMS = 6;        // 256*6 = 1536 >= 1024+273
@@ -239,64 +238,74 @@ __device__ __forceinline__ double pwr(const void* __restrict__ iq, size_t i) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(SP_THREADS) sp_partial_kernel(const void* __restrict__ iq, double* __restrict__ sp_partial,
-                                                                const uint32_t n_cap, const uint32_t n_comb_sp) {
+__global__ void __launch_bounds__(SP_THREADS) sp_fold_kernel(const void* __restrict__ iq, double* __restrict__ sp_incoherent,
+                                                             const uint32_t n_cap, const uint32_t n_comb_sp) {
   __shared__ double ps[SP_THREADS * SP_ITEMS + 1];   // exclusive prefix sums
   __shared__ double wsum[SP_THREADS / 32];
-  const uint32_t m = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  const uint32_t b = blockIdx.y, tid = threadIdx.x;
   const uint32_t i_base = blockIdx.x * SP_TILE;
-  const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
-  const uint32_t n_need = min((uint32_t)SP_TILE, LCS_N_FOLD - i_base) + 273;   // samples this block touches (all < n_cap)
-  double v[SP_ITEMS], run = 0;
+  const uint32_t n_pos = min((uint32_t)SP_TILE, LCS_N_FOLD - i_base);
+  const uint32_t n_need = n_pos + 273;               // samples this block touches per half frame (all < n_cap)
+  double acc[SP_TILE / SP_THREADS];
+  for (uint32_t m = 0; m < n_comb_sp; m++) {
+    const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
+    double v[SP_ITEMS], run = 0;
 #pragma unroll
-  for (int k = 0; k < SP_ITEMS; k++) {
-    const uint32_t e = tid * SP_ITEMS + k;
-    v[k] = e < n_need ? pwr<FMT>(iq, base + e) : 0.0;
-    run += v[k];
-  }
-  // block exclusive scan of the per-thread totals
-  double incl = run;
+    for (int k = 0; k < SP_ITEMS; k++) {
+      const uint32_t e = tid * SP_ITEMS + k;
+      v[k] = e < n_need ? pwr<FMT>(iq, base + e) : 0.0;
+      run += v[k];
+    }
+    // block exclusive scan of the per-thread totals
+    double incl = run;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= (uint32_t)o) incl += t;
-  }
-  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
-  __syncthreads();
-  double woff = 0;
-  for (uint32_t w = 0; w < (tid >> 5); w++) woff += wsum[w];
-  double acc = woff + incl - run;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();                                 // the previous half frame's prefix sums have been consumed
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    double woff = 0;
+    for (uint32_t w = 0; w < (tid >> 5); w++) woff += wsum[w];
+    double a = woff + incl - run;
 #pragma unroll
-  for (int k = 0; k < SP_ITEMS; k++) {
-    ps[tid * SP_ITEMS + k] = acc;
-    acc += v[k];
+    for (int k = 0; k < SP_ITEMS; k++) {
+      ps[tid * SP_ITEMS + k] = a;
+      a += v[k];
+    }
+    if (tid == SP_THREADS - 1) ps[SP_THREADS * SP_ITEMS] = a;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SP_TILE / SP_THREADS; k++) {
+      const uint32_t i = tid + k * SP_THREADS;
+      const double sp = (ps[i + 274] - ps[i]) / 274;
+      acc[k] = m == 0 ? sp : acc[k] + sp;            // searcher.cpp:213-216: sp_incoherent = sp(0..9599) + sp(9600..) + ...
+    }
   }
-  if (tid == SP_THREADS - 1) ps[SP_THREADS * SP_ITEMS] = acc;
-  __syncthreads();
-  double* dst = sp_partial + ((size_t)b * n_comb_sp + m) * LCS_N_FOLD + i_base;
-  for (uint32_t i = tid; i < SP_TILE && i_base + i < LCS_N_FOLD; i += SP_THREADS) dst[i] = (ps[i + 274] - ps[i]) / 274;
+#pragma unroll
+  for (int k = 0; k < SP_TILE / SP_THREADS; k++) {
+    const uint32_t i = tid + k * SP_THREADS;
+    if (i < n_pos) sp_incoherent[(size_t)b * LCS_N_FOLD + (i_base + i + 137) % LCS_N_FOLD] = acc[k] / n_comb_sp;   // :217-220
+  }
 }
 
-int launch_sp_partial(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_partial,
-                      cudaStream_t st) {
-  dim3 grid((LCS_N_FOLD + SP_TILE - 1) / SP_TILE, g.n_comb_sp, batch);
-#define CALL(F) sp_partial_kernel<F><<<grid, SP_THREADS, 0, st>>>(d_iq, d_sp_partial, g.n_cap, g.n_comb_sp)
+int launch_sp_fold(const XcorrGeom& g, const void* d_iq, int iq_format, uint32_t batch, double* d_sp_incoherent, cudaStream_t st) {
+  dim3 grid((LCS_N_FOLD + SP_TILE - 1) / SP_TILE, batch);
+#define CALL(F) sp_fold_kernel<F><<<grid, SP_THREADS, 0, st>>>(d_iq, d_sp_incoherent, g.n_cap, g.n_comb_sp)
   LCS_DISPATCH_FMT(iq_format, CALL);
 #undef CALL
   return 1;
 }
 
 // ------------------------------------------------------------------------------------------
-// Epilogue: xc_delay_spread (searcher.cpp:312-347) + xc_peak_freq (:353-383) + the sp fold and
-// tshift(sp_incoherent,137) of sp_est (:213-220).  One thread per (t, idx); planar reads are
-// coalesced along idx.
+// Epilogue: xc_delay_spread (searcher.cpp:312-347) + xc_peak_freq (:353-383).  One thread per (t, idx); planar reads
+// are coalesced along idx.  HBM-bound: every value of xc_incoherent_single is read once.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__ single_planar,
-                                                       const double* __restrict__ sp_partial, double* __restrict__ pow_out,
-                                                       int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
-                                                       float* __restrict__ incoherent_planar, const uint32_t n_f_stride,
-                                                       const int* __restrict__ plan_nf, const uint32_t* __restrict__ buf_plan,
-                                                       const uint32_t arm, const uint32_t n_comb_sp) {
+__global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__ single_planar, double* __restrict__ pow_out,
+                                                       int32_t* __restrict__ frq_out, float* __restrict__ incoherent_planar,
+                                                       const uint32_t n_f_stride, const int* __restrict__ plan_nf,
+                                                       const uint32_t* __restrict__ buf_plan, const uint32_t arm) {
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
   if (idx >= LCS_N_FOLD) return;
   const uint32_t n_f = (uint32_t)__ldg(plan_nf + (buf_plan ? __ldg(buf_plan + b) : 0u));
@@ -320,26 +329,21 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__
   }
   pow_out[((size_t)b * 3 + t) * LCS_N_FOLD + idx] = (double)best;
   frq_out[((size_t)b * 3 + t) * LCS_N_FOLD + idx] = best_f;
-  if (t == 0) {
-    const double* sp = sp_partial + (size_t)b * n_comb_sp * LCS_N_FOLD;
-    double acc = sp[idx];
-    for (uint32_t m = 1; m < n_comb_sp; m++) acc += sp[(size_t)m * LCS_N_FOLD + idx];
-    sp_incoherent[(size_t)b * LCS_N_FOLD + (idx + 137) % LCS_N_FOLD] = acc / n_comb_sp;
-  }
 }
 
-// Vectorised variant for ds_comb_arm <= 4: one thread = 4 consecutive fold positions, three 128-bit
-// loads per hypothesis (previous / own / next quad; 9600 % 4 == 0 so the circular wrap is a quad index wrap).
+// Vectorised variant for ds_comb_arm <= 4: one thread = 4 consecutive fold positions, ONE 128-bit load per hypothesis;
+// the neighbours' edge values come from the adjacent lanes (warp shuffles), only the first and the last lane of a warp
+// fetch the halo of the neighbouring warp themselves (9600 % 4 == 0 so the circular wrap is a quad index wrap).  The f
+// loop is unrolled so that several hypotheses' loads are in flight per thread.
 template <int ARM>
-__global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict__ single_planar,
-                                                        const double* __restrict__ sp_partial, double* __restrict__ pow_out,
-                                                        int32_t* __restrict__ frq_out, double* __restrict__ sp_incoherent,
-                                                        float* __restrict__ incoherent_planar, const uint32_t n_f_stride,
-                                                        const int* __restrict__ plan_nf, const uint32_t* __restrict__ buf_plan,
-                                                        const uint32_t n_comb_sp) {
-  constexpr uint32_t NQ = LCS_N_FOLD / 4;
+__global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict__ single_planar, double* __restrict__ pow_out,
+                                                        int32_t* __restrict__ frq_out, float* __restrict__ incoherent_planar,
+                                                        const uint32_t n_f_stride, const int* __restrict__ plan_nf,
+                                                        const uint32_t* __restrict__ buf_plan) {
+  constexpr uint32_t NQ = LCS_N_FOLD / 4;      // 2400 quads = 75 warps exactly
   const uint32_t q = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
-  if (q >= NQ) return;
+  if (q >= NQ) return;                          // whole warps only (2400 = 75 * 32)
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t n_f = (uint32_t)__ldg(plan_nf + (buf_plan ? __ldg(buf_plan + b) : 0u));
   const uint32_t qp = q == 0 ? NQ - 1 : q - 1, qn = q == NQ - 1 ? 0 : q + 1;
   const float4* s = reinterpret_cast<const float4*>(single_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD);
@@ -347,17 +351,24 @@ __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict_
   const float denom = (float)(2 * ARM + 1);
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int best_f[4] = {0, 0, 0, 0};
-#pragma unroll 2
+#pragma unroll 4
   for (uint32_t f = 0; f < n_f; f++) {
     const float4* sf = s + (size_t)f * NQ;
     const float4 c = __ldg(sf + q);
     float w[12];
+    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
     if (ARM > 0) {
-      const float4 pv = __ldg(sf + qp), nx = __ldg(sf + qn);
+      // previous quad from lane-1, next quad from lane+1
+      float4 pv, nx;
+      pv.x = __shfl_up_sync(0xffffffffu, c.x, 1); pv.y = __shfl_up_sync(0xffffffffu, c.y, 1);
+      pv.z = __shfl_up_sync(0xffffffffu, c.z, 1); pv.w = __shfl_up_sync(0xffffffffu, c.w, 1);
+      nx.x = __shfl_down_sync(0xffffffffu, c.x, 1); nx.y = __shfl_down_sync(0xffffffffu, c.y, 1);
+      nx.z = __shfl_down_sync(0xffffffffu, c.z, 1); nx.w = __shfl_down_sync(0xffffffffu, c.w, 1);
+      if (lane == 0) pv = __ldg(sf + qp);
+      if (lane == 31) nx = __ldg(sf + qn);
       w[0] = pv.x; w[1] = pv.y; w[2] = pv.z; w[3] = pv.w;
       w[8] = nx.x; w[9] = nx.y; w[10] = nx.z; w[11] = nx.w;
     }
-    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
     float v[4];
 #pragma unroll
     for (int o = 0; o < 4; o++) {
@@ -374,25 +385,13 @@ __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict_
   reinterpret_cast<double2*>(pow_out + o0)[0] = make_double2((double)best[0], (double)best[1]);
   reinterpret_cast<double2*>(pow_out + o0)[1] = make_double2((double)best[2], (double)best[3]);
   *reinterpret_cast<int4*>(frq_out + o0) = make_int4(best_f[0], best_f[1], best_f[2], best_f[3]);
-  if (t == 0) {
-    const double* sp = sp_partial + (size_t)b * n_comb_sp * LCS_N_FOLD;
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-      const uint32_t idx = 4 * q + o;
-      double acc = sp[idx];
-      for (uint32_t m = 1; m < n_comb_sp; m++) acc += sp[(size_t)m * LCS_N_FOLD + idx];
-      sp_incoherent[(size_t)b * LCS_N_FOLD + (idx + 137) % LCS_N_FOLD] = acc / n_comb_sp;
-    }
-  }
 }
 
-int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, const float* d_single_planar,
-                    const double* d_sp_partial, double* d_pow, int32_t* d_frq, double* d_sp_incoherent,
-                    float* d_incoherent_planar, cudaStream_t st) {
+int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, const float* d_single_planar, double* d_pow,
+                    int32_t* d_frq, float* d_incoherent_planar, cudaStream_t st) {
   if (g.ds_comb_arm <= 4) {
     dim3 grid((LCS_N_FOLD / 4 + 127) / 128, 3, batch);
-#define EPI(A) epilogue4_kernel<A><<<grid, 128, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent, \
-                                                     d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan, g.n_comb_sp)
+#define EPI(A) epilogue4_kernel<A><<<grid, 128, 0, st>>>(d_single_planar, d_pow, d_frq, d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan)
     switch (g.ds_comb_arm) {
       case 0: EPI(0); break;
       case 1: EPI(1); break;
@@ -404,8 +403,7 @@ int launch_epilogue(const XcorrGeom& g, const PlanView& pv, uint32_t batch, cons
     return 1;
   }
   dim3 grid((LCS_N_FOLD + 255) / 256, 3, batch);
-  epilogue_kernel<<<grid, 256, 0, st>>>(d_single_planar, d_sp_partial, d_pow, d_frq, d_sp_incoherent,
-                                        d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan, g.ds_comb_arm, g.n_comb_sp);
+  epilogue_kernel<<<grid, 256, 0, st>>>(d_single_planar, d_pow, d_frq, d_incoherent_planar, g.n_f_stride, pv.d_nf, pv.d_buf_plan, g.ds_comb_arm);
   return 1;
 }
 

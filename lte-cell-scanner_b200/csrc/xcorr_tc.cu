@@ -45,6 +45,9 @@
 #ifndef LCS_TC_PROFILE
 #define LCS_TC_PROFILE 0
 #endif
+#ifndef LCS_TC_LD1
+#define LCS_TC_LD1 0     // 1: all three digit planes of a part in one tcgen05.ld round (more registers live)
+#endif
 #if LCS_TC_PROFILE
 #define TC_CLK() clock64()
 #else
@@ -66,6 +69,7 @@ struct TcParams {
   uint32_t tu, t_cta;         // tiles per unit / tiles per CTA
   uint32_t n_tiles_total;     // n_units * tu
   float inv2s;                // 1 / (S*128)^2
+  float rcp_ncomb;            // RN(1 / n_comb) when the 3-instruction division is exact for n_comb, else 0
   long long* prof;            // optional [grid][12] cycle counters (NULL = off)
 };
 
@@ -80,16 +84,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait parks the warp until the phase completes or the suspend-time hint (ns) expires: without a hint the hardware
+// limit is short and the epilogue warps spent ~15 % of the SM's issue slots polling (ncu r02c: SYNCS + BRA + YIELD)
+#ifndef LCS_TC_WAIT_HINT_NS
+#define LCS_TC_WAIT_HINT_NS 2000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE;\n"
       "bra WAIT_LOOP;\n"
       "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "r"(LCS_TC_WAIT_HINT_NS)
       : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
@@ -422,6 +431,15 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
       t_fwait += c1 - c0;
       tc_fence_after();
       const uint32_t src = lane_base + slot * NJOB;
+#if LCS_TC_LD1
+      int a1[NC];
+      tmem_ld16(src, t);
+      tmem_ld16(src + C, a1);
+      tmem_ld16(src + 2 * C, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a1[c];
+#else
       tmem_ld16(src, t);
       tmem_ld16(src + C, a);
       tmem_ld_wait();
@@ -429,6 +447,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
       for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
       tmem_ld16(src + 2 * C, a);
       tmem_ld_wait();
+#endif
       t_ld += TC_CLK() - c1;
       tc_fence_before();
       __syncwarp();
@@ -497,7 +516,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
         // youngest carry over to the next tile of the run ----
         long long c0 = TC_CLK();
         epi_bar(32 * N_EPI_WARPS);
-        const float ncf = (float)p.n_comb;
+        const float ncf = (float)p.n_comb, rcp = p.rcp_ncomb;
         const int pb = r.p0 + (int)(tc::NT * k) - tc::HALO;       // fold position of window index 0
         const bool last = k + 1 == r.n_tiles;
         for (uint32_t row = ewarp; row < n_templ; row += N_EPI_WARPS) {
@@ -508,7 +527,17 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
           for (int j = lane; j < tc::NT; j += 32) {
             const int pos = pb + j;
             const float v = src[j];
-            if (pos >= r.p0 && pos < r.p1) dst[pos] = __fdiv_rn(__fmul_rn(v, p.inv2s), ncf);   // searcher.cpp:304
+            if (pos >= r.p0 && pos < r.p1) {                                                  // searcher.cpp:304: sum / n_comb
+              const float x = __fmul_rn(v, p.inv2s);                                          // power-of-two scale: exact
+              float qv;
+              if (rcp != 0.f) {        // q = RN(x * r), one Newton step: correctly rounded for these divisors (tools/divchk.c)
+                qv = __fmul_rn(x, rcp);
+                qv = __fmaf_rn(__fmaf_rn(-ncf, qv, x), rcp, qv);
+              } else {
+                qv = __fdiv_rn(x, ncf);
+              }
+              dst[pos] = qv;
+            }
           }
           const float carry = last ? 0.f : src[tc::NT + lane];
           __syncwarp();
@@ -590,6 +619,11 @@ int launch_xcorr_fold_tc(PlanSet& ps, const void* d_iq_cu8, uint32_t batch, cons
   q.batch = batch;
   q.n_pass = ps.n_pass;
   q.inv2s = ps.inv_scale * ps.inv_scale;
+  // x / n by  q = RN(x*r); q += RN(x - n*q) * r  (r = RN(1/n)) equals the IEEE quotient for EVERY non-negative float x for
+  // these n (exhaustive check, tools/divchk.c); other divisors use the division instruction sequence
+  static const bool kExactRcp[25] = {false, true, true, true, true, true, false, true, true, true, false, true, false,
+                                     true, false, true, true, true, false, true, false, true, false, true, false};
+  q.rcp_ncomb = (g.n_comb_xc <= 24 && kExactRcp[g.n_comb_xc]) ? 1.0f / (float)g.n_comb_xc : 0.f;
   q.prof = tc_prof_buffer();
   // tiles per unit: T tiles of a run give 256 T - 32 positions, and a unit is cut into at most ceil(tu / t_cta) + 1 runs
   const uint32_t n_units = batch * ps.n_pass, n_sm = (uint32_t)ps.ctx->n_sm;
