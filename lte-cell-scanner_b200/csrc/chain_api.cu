@@ -1,6 +1,9 @@
 // chain_api.cu - C-ABI entry points for the stages after xcorr_pss (include/lcs_b200.h).
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "chain_gpu.hpp"
 
@@ -38,19 +41,24 @@ static std::vector<cd> from_colmajor(const double* in, int n_rows, int n_cols) {
 
 // Per-peak stages of CellSearch.cpp:510-558 (sss_detect -> pss_sss_foe -> extract_tfg -> tfoec -> decode_mib) on a
 // device-resident capture buffer; cells that fail the SSS or MIB tests are dropped like in the reference.
+// Two phases: the device stages run peak by peak on the context's stream; the host stages (tfoec, chan_est, PBCH decoding
+// with its 12 tail-biting Viterbi attempts - milliseconds per cell) of all surviving peaks then run on parallel threads.
 lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_cap, const std::vector<lcs_cell>& pk, double fc_req,
                           double fc_prog, double fs_prog, lcs_cell* cells, uint32_t max_cells, uint32_t* n_cells,
                           const int32_t* tracked, uint32_t n_tracked, bool tracker_cycle) {
   const double THRESH2_N_SIGMA = 3;     // CellSearch.cpp:528
   lcs_status rc = LCS_OK;
-  if (pk.empty()) {
-    if (n_cells) *n_cells = 0;
-    return LCS_OK;
-  }
+  if (n_cells) *n_cells = 0;
+  if (pk.empty()) return LCS_OK;
   ChainScratch& cs = chain_scratch(ctx);
-  uint32_t found = 0;
-  const bool tracked_mode = tracker_cycle;
-  std::vector<int> accepted_ids;
+  struct Pending {
+    lcs_cell c;                      // after pss_sss_foe
+    std::vector<cd> tfg;
+    std::vector<double> ts;
+    lcs_cell out;                    // after decode_mib
+  };
+  std::vector<Pending> pend;
+  pend.reserve(pk.size());
   for (lcs_cell c : pk) {
     lcs_cell o;
     rc = dev_sss_detect(ctx, cs, d_cap, fmt, n_cap, c, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, o, nullptr);
@@ -58,31 +66,52 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
     if (rc != LCS_OK) return rc;
     if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
     c = o;
-    // searcher_thread.cpp:153-174: cells that are being tracked are not examined further.  The reference appends every new
-    // cell to tracked_cell_list inside this loop (:216-219), so a later peak of the same buffer with the same id is skipped too.
+    // searcher_thread.cpp:153-174: cells that are being tracked are not examined further
     bool already_tracked = false;
     for (uint32_t k = 0; k < n_tracked; k++) already_tracked |= tracked[k] == c.n_id_2 + 3 * c.n_id_1;
-    if (tracked_mode)
-      for (int id : accepted_ids) already_tracked |= id == c.n_id_2 + 3 * c.n_id_1;
     if (already_tracked) continue;
     rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
     if (rc != LCS_OK) return rc;
     c = o;
-    std::vector<cd> tfg, tfg_comp;
-    std::vector<double> ts, ts_comp;
-    rc = dev_extract_tfg(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, tfg, ts);
+    Pending q;
+    rc = dev_extract_tfg(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, q.tfg, q.ts);
     if (rc == LCS_ERR_RANGE) continue;
     if (rc != LCS_OK) return rc;
-    RsDl rs(c.n_id_2 + 3 * c.n_id_1, c.cp_type);  // CellSearch.cpp:545
-    tfg_comp.resize(tfg.size());
-    ts_comp.resize(ts.size());
-    tfoec(c, tfg.data(), ts.data(), (int)ts.size(), fc_req, fc_prog, rs, tfg_comp.data(), ts_comp.data(), o);
-    c = o;
-    decode_mib(c, tfg_comp.data(), (int)ts.size(), rs, o);
-    if (o.n_rb_dl == -1) continue;  // CellSearch.cpp:554-558
-    if (found < max_cells && cells) cells[found] = o;
+    q.c = c;
+    pend.push_back(std::move(q));
+  }
+  auto host_stage = [&](Pending& q) {
+    RsDl rs(q.c.n_id_2 + 3 * q.c.n_id_1, q.c.cp_type);  // CellSearch.cpp:545
+    std::vector<cd> tfg_comp(q.tfg.size());
+    std::vector<double> ts_comp(q.ts.size());
+    lcs_cell o;
+    tfoec(q.c, q.tfg.data(), q.ts.data(), (int)q.ts.size(), fc_req, fc_prog, rs, tfg_comp.data(), ts_comp.data(), o);
+    decode_mib(o, tfg_comp.data(), (int)q.ts.size(), rs, q.out);
+  };
+  if (pend.size() <= 1) {
+    for (Pending& q : pend) host_stage(q);
+  } else {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_thr = std::min<size_t>(pend.size(), hw);
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; t++)
+      pool.emplace_back([&] {
+        for (size_t i = next.fetch_add(1); i < pend.size(); i = next.fetch_add(1)) host_stage(pend[i]);
+      });
+    for (std::thread& th : pool) th.join();
+  }
+  // In tracker mode the reference appends every new cell to tracked_cell_list inside its peak loop
+  // (searcher_thread.cpp:216-219): a later peak of the same buffer that decodes to an id accepted earlier is skipped.
+  uint32_t found = 0;
+  std::vector<int> accepted_ids;
+  for (Pending& q : pend) {
+    if (q.out.n_rb_dl == -1) continue;  // CellSearch.cpp:554-558
+    const int id = q.out.n_id_2 + 3 * q.out.n_id_1;
+    if (tracker_cycle && std::find(accepted_ids.begin(), accepted_ids.end(), id) != accepted_ids.end()) continue;
+    if (found < max_cells && cells) cells[found] = q.out;
     found++;
-    accepted_ids.push_back(o.n_id_2 + 3 * o.n_id_1);
+    accepted_ids.push_back(id);
   }
   if (n_cells) *n_cells = found;
   return LCS_OK;

@@ -305,7 +305,10 @@ lcs_status dev_sss_detect(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, int
   if (rc != LCS_OK) return rc;
   LCS_CUDA(ctx, cs.d_est.ensure(124 + 4 * 124));
   LCS_CUDA(ctx, cs.d_ll.ensure(4 * 168));
-  LCS_CUDA(ctx, cudaFuncSetAttribute(sss_getce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAX_PSS * 62 * (int)sizeof(double2)));
+  if (!cs.getce_attr_set) {
+    LCS_CUDA(ctx, cudaFuncSetAttribute(sss_getce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAX_PSS * 62 * (int)sizeof(double2)));
+    cs.getce_attr_set = true;
+  }
   sss_getce_kernel<<<1, 64, (size_t)2 * n_pss * 62 * sizeof(double2), st>>>(cs.d_psss.p, n_pss, cs.d_pss_fd.p + cell.n_id_2 * 62, cs.d_est.p);
   sss_ml_kernel<<<168, 128, 0, st>>>(cs.d_est.p, cs.d_sss_tab.p, cell.n_id_2, cs.d_ll.p);
   ctx->launches += 2;

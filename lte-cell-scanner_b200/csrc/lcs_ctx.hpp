@@ -116,6 +116,8 @@ struct lcs_xcorr_plan {
   // kernel timing hook
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_used;
+  double ev_acc_ms = 0;                        // time of event pairs already harvested from ev_used
+  uint64_t ev_acc_n = 0;
   // per-stream device buffers of the host-batch entry points
   struct HostBatchBufs {
     lcs::DevBuf<unsigned char> iq;

@@ -56,20 +56,22 @@ void pss_td(int n_id_2, cd out[137]) {
 
 // SSS in the frequency domain as +-1 integers.  Reference: src/lte_lib.cpp:199-257 (3GPP 36.211 6.11.2).
 void sss_fd(int n_id_1, int n_id_2, int slot, int out[62]) {
-  static int s_t[31], c_t[31], z_t[31];
-  static bool init = false;
-  if (!init) {
-    int x[31];
-    auto gen = [&](int* dst, auto rec) {
-      for (int i = 0; i < 5; i++) x[i] = (i == 4);
-      for (int i = 0; i < 26; i++) x[i + 5] = rec(x, i) & 1;
-      for (int i = 0; i < 31; i++) dst[i] = 1 - 2 * x[i];
-    };
-    gen(s_t, [](const int* v, int i) { return v[i + 2] + v[i]; });                       // x^5+x^2+1
-    gen(c_t, [](const int* v, int i) { return v[i + 3] + v[i]; });                       // x^5+x^3+1
-    gen(z_t, [](const int* v, int i) { return v[i + 4] + v[i + 2] + v[i + 1] + v[i]; });  // x^5+x^4+x^2+x+1
-    init = true;
-  }
+  struct Tab {      // the three m-sequences, built once (thread-safe static initialisation)
+    int s[31], c[31], z[31];
+    Tab() {
+      int x[31];
+      auto gen = [&](int* dst, auto rec) {
+        for (int i = 0; i < 5; i++) x[i] = (i == 4);
+        for (int i = 0; i < 26; i++) x[i + 5] = rec(x, i) & 1;
+        for (int i = 0; i < 31; i++) dst[i] = 1 - 2 * x[i];
+      };
+      gen(s, [](const int* v, int i) { return v[i + 2] + v[i]; });                       // x^5+x^2+1
+      gen(c, [](const int* v, int i) { return v[i + 3] + v[i]; });                       // x^5+x^3+1
+      gen(z, [](const int* v, int i) { return v[i + 4] + v[i + 2] + v[i + 1] + v[i]; });  // x^5+x^4+x^2+x+1
+    }
+  };
+  static const Tab tab;
+  const int *s_t = tab.s, *c_t = tab.c, *z_t = tab.z;
   const int qp = n_id_1 / 30;
   const int q = (n_id_1 + qp * (qp + 1) / 2) / 30;
   const int mp = n_id_1 + q * (q + 1) / 2;

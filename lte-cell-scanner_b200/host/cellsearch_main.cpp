@@ -37,6 +37,7 @@ static void print_usage() {
   cout << "  -l --load                      read captured data from capbuf_XXXX.it files" << endl;
   cout << "  -d --data-dir dir              directory of the capbuf_XXXX.it files" << endl;
   cout << "     --raw                       with -l: read capbuf_XXXX.bin raw rtl_sdr byte dumps instead" << endl;
+  cout << "     --sweep                     with -l --raw: all centre frequencies in one batched call (lcs_sweep_search_cu8)" << endl;
   cout << "  -r --record / -i --device-index need a live rtl-sdr dongle: not supported by this build" << endl;
 }
 
@@ -53,13 +54,13 @@ static string freq_formatter(const double& freq) {   // CellSearch.cpp:322-341
 
 int main(int argc, char* const argv[]) {
   double freq_start = -1, freq_end = -1, ppm = 120, correction = 1;
-  bool save_cap = false, use_recorded_data = false, raw = false;
+  bool save_cap = false, use_recorded_data = false, raw = false, batched = false;
   string data_dir = ".";
   static struct option long_options[] = {
       {"help", no_argument, 0, 'h'},          {"verbose", no_argument, 0, 'v'},       {"brief", no_argument, 0, 'b'},
       {"freq-start", required_argument, 0, 's'}, {"freq-end", required_argument, 0, 'e'}, {"ppm", required_argument, 0, 'p'},
       {"correction", required_argument, 0, 'c'}, {"record", no_argument, 0, 'r'},        {"load", no_argument, 0, 'l'},
-      {"data-dir", required_argument, 0, 'd'},   {"device-index", required_argument, 0, 'i'}, {"raw", no_argument, 0, 'R'},
+      {"data-dir", required_argument, 0, 'd'},   {"device-index", required_argument, 0, 'i'}, {"raw", no_argument, 0, 'R'}, {"sweep", no_argument, 0, 'W'},
       {0, 0, 0, 0}};
   for (;;) {
     int idx = 0;
@@ -78,6 +79,7 @@ int main(int argc, char* const argv[]) {
       case 'l': use_recorded_data = true; break;
       case 'd': data_dir = optarg; break;
       case 'R': raw = true; break;
+      case 'W': batched = true; break;
       case 'i': break;
       default: return -1;
     }
@@ -121,7 +123,35 @@ int main(int argc, char* const argv[]) {
     const int n_fc = (int)floor((freq_end - freq_start) / 100e3) + 1;                   // :465
     vector<list<Cell> > detected_cells(n_fc);
     xcorr_pss_skip_debug_outputs(true);
-    for (int fci = 0; fci < n_fc; fci++) {
+    if (batched) {
+      // every centre frequency of the sweep in one call: the raw byte dumps are concatenated and handed to the batched
+      // search (same per-channel results as the loop below, CellSearch.cpp:465-558)
+      if (!raw) { cerr << "Error: --sweep needs --raw capture files" << endl; return -1; }
+      vector<unsigned char> all;
+      vector<double> fcs;
+      uint32_t n_cap = 0;
+      for (int fci = 0; fci < n_fc; fci++) {
+        stringstream filename;
+        filename << data_dir << "/capbuf_" << setw(4) << setfill('0') << fci << ".bin";
+        vector<unsigned char> b;
+        if (!lcs_it::read_all(filename.str(), b) || b.size() < 2) { cerr << "Error: cannot read " << filename.str() << endl; return -1; }
+        if (fci == 0) n_cap = (uint32_t)(b.size() / 2);
+        if (b.size() / 2 != n_cap) { cerr << "Error: capture buffers of a batched sweep must have equal length" << endl; return -1; }
+        all.insert(all.end(), b.begin(), b.begin() + (size_t)n_cap * 2);
+        fcs.push_back(freq_start + fci * 100e3);
+      }
+      if (verbosity >= 1) cout << "Examining " << n_fc << " center frequencies in one batched sweep ..." << endl;
+      sweep_search_cu8(all, n_cap, fcs, f_search_set, fs_programmed, detected_cells);
+      if (verbosity >= 1)
+        for (int fci = 0; fci < n_fc; fci++)
+          for (list<Cell>::iterator it = detected_cells[fci].begin(); it != detected_cells[fci].end(); ++it) {
+            cout << "  Detected a cell!" << endl;
+            cout << "    cell ID: " << (*it).n_id_cell() << endl;
+            cout << "    RX power level: " << 10 * log10((*it).pss_pow) << " dB" << endl;
+            cout << "    residual frequency offset: " << (*it).freq_superfine << " Hz" << endl;
+          }
+    }
+    for (int fci = 0; fci < (batched ? 0 : n_fc); fci++) {
       const double fc_requested = freq_start + fci * 100e3;
       if (verbosity >= 1) cout << "Examining center frequency " << fc_requested / 1e6 << " MHz ..." << endl;
       cvec capbuf;

@@ -63,6 +63,23 @@ static Cell from_pod(const lcs_cell& p) {
   return c;
 }
 
+void sweep_search_cu8(const std::vector<unsigned char>& iq, uint32_t n_cap, const std::vector<double>& fc_requested,
+                      const vec& f_search_set, const double& fs_programmed, std::vector<std::list<Cell> >& detected_cells) {
+  const uint32_t n_ch = (uint32_t)fc_requested.size(), max_cells = 16;
+  if (iq.size() < (size_t)n_ch * n_cap * 2) throw("sweep_search_cu8: capture data shorter than n_fc buffers");
+  lcs_sweep* sw = nullptr;
+  check(lcs_sweep_create(lcs_dropin_ctx(), n_cap, &sw), "lcs_sweep_create");
+  std::vector<lcs_cell> cells((size_t)n_ch * max_cells);
+  std::vector<uint32_t> n(n_ch, 0);
+  lcs_status rc = lcs_sweep_search_cu8(sw, iq.data(), n_ch, fc_requested.data(), nullptr, fs_programmed, f_search_set._data(),
+                                       (uint32_t)f_search_set.length(), cells.data(), max_cells, n.data());
+  lcs_sweep_destroy(sw);
+  check(rc, "lcs_sweep_search_cu8");
+  detected_cells.assign(n_ch, std::list<Cell>());
+  for (uint32_t c = 0; c < n_ch; c++)
+    for (uint32_t k = 0; k < n[c] && k < max_cells; k++) detected_cells[c].push_back(from_pod(cells[(size_t)c * max_cells + k]));
+}
+
 // ---- searcher.h:22-41 ----
 void xcorr_pss(const cvec& capbuf, const vec& f_search_set, const uint8& ds_comb_arm, const double& fc_requested,
                const double& fc_programmed, const double& fs_programmed, mat& xc_incoherent_collapsed_pow,

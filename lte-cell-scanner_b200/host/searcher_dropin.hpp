@@ -91,4 +91,9 @@ void dedup(const std::vector<std::list<Cell> >& detected_cells, std::list<Cell>&
 itpp::vec calc_Z_th1(const itpp::vec& sp_incoherent, uint16 n_comb_xc, uint8 ds_comb_arm);         // CellSearch.cpp:500-503
 // CUDA device used by the drop-in (default 0, or env LCS_DEVICE); created lazily, process-wide.
 lcs_ctx* lcs_dropin_ctx();
-void xcorr_pss_skip_debug_outputs(bool skip);   // skip the 136 MB `xc`/`sp`/`xc_incoherent` debug outputs (CLI does)
+void xcorr_pss_skip_debug_outputs(bool skip);
+// The whole per-centre-frequency loop of CellSearch.cpp:465-558 for raw 8-bit capture buffers (cu8 [n_fc][n_cap][2]) in one call:
+// lcs_sweep_search_cu8 (one plan per centre frequency, one correlator launch per 64 channels).  detected_cells as in :469.
+void sweep_search_cu8(const std::vector<unsigned char>& iq, uint32_t n_cap, const std::vector<double>& fc_requested,
+                      const itpp::vec& f_search_set, const double& fs_programmed, std::vector<std::list<Cell> >& detected_cells);
+   // skip the 136 MB `xc`/`sp`/`xc_incoherent` debug outputs (CLI does)

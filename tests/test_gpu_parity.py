@@ -559,3 +559,26 @@ def test_stream_search_cli_kalibrate(ctx, tmp_path, capbuf0000):
     m = re.search(r"Residual frequency offset: ([0-9.]+) Hz", out.stdout)
     assert m and abs(float(m.group(1)) - 35228.46) < 0.5
     assert re.search(r"new cell 277 ", out.stdout)
+
+
+def test_cellsearch_cli_batched_sweep(ctx, tmp_path, capbuf0000):
+    """`CellSearch_b200 -s 738.9M -e 739.1M -l --raw --sweep`: three centre frequencies through lcs_sweep_search_cu8 print
+    the same table rows as the one-frequency-at-a-time loop (cells 277 and 271 at 739.0 MHz)."""
+    import os
+    import re
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    host = os.path.join(root, "lte-cell-scanner_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    synth_cu8(11).tofile(str(tmp_path / "capbuf_0000.bin"))
+    capbuf0000["cu8"].tofile(str(tmp_path / "capbuf_0001.bin"))
+    synth_cu8(12).tofile(str(tmp_path / "capbuf_0002.bin"))
+    outs = []
+    for extra in ([], ["--sweep"]):
+        out = subprocess.run([os.path.join(host, "CellSearch_b200"), "-s", "738900000", "-e", "739100000", "-l", "--raw", "-b",
+                              "-d", str(tmp_path)] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr + out.stdout
+        rows = [l for l in out.stdout.splitlines() if re.match(r"^\s*27[17]\s+2\s", l)]
+        assert len(rows) == 2
+        outs.append(rows)
+    assert outs[0] == outs[1]
