@@ -237,38 +237,54 @@ __device__ __forceinline__ double pwr(const void* __restrict__ iq, size_t i) {
   return (double)v.x * (double)v.x + (double)v.y * (double)v.y;
 }
 
+// Element type of the prefix scan: for raw 8-bit IQ the sample power (I-127)^2 + (Q-127)^2 is an integer <= 2*128^2 and a
+// prefix sum over a tile (< 2^26) fits int32, so the scan runs in integers (exact, a third of the FP64 instructions);
+// sp = isum * 2^-14 / 274 is then the same exactly rounded quotient the reference's double recursion produces.
+template <int FMT> struct SpAcc { typedef double T; };
+template <> struct SpAcc<LCS_IQ_CU8> { typedef int T; };
+template <int FMT>
+__device__ __forceinline__ typename SpAcc<FMT>::T sp_term(const void* __restrict__ iq, size_t i) { return pwr<FMT>(iq, i); }
+template <>
+__device__ __forceinline__ int sp_term<LCS_IQ_CU8>(const void* __restrict__ iq, size_t i) {
+  const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(iq) + i);
+  const int a = (int)v.x - 127, b = (int)v.y - 127;
+  return a * a + b * b;
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(SP_THREADS) sp_fold_kernel(const void* __restrict__ iq, double* __restrict__ sp_incoherent,
                                                              const uint32_t n_cap, const uint32_t n_comb_sp) {
-  __shared__ double ps[SP_THREADS * SP_ITEMS + 1];   // exclusive prefix sums
-  __shared__ double wsum[SP_THREADS / 32];
+  typedef typename SpAcc<FMT>::T T;
+  __shared__ T ps[SP_THREADS * SP_ITEMS + 1];   // exclusive prefix sums
+  __shared__ T wsum[SP_THREADS / 32];
   const uint32_t b = blockIdx.y, tid = threadIdx.x;
   const uint32_t i_base = blockIdx.x * SP_TILE;
   const uint32_t n_pos = min((uint32_t)SP_TILE, LCS_N_FOLD - i_base);
   const uint32_t n_need = n_pos + 273;               // samples this block touches per half frame (all < n_cap)
+  const double unit = FMT == LCS_IQ_CU8 ? 1.0 / 16384.0 : 1.0;
   double acc[SP_TILE / SP_THREADS];
   for (uint32_t m = 0; m < n_comb_sp; m++) {
     const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
-    double v[SP_ITEMS], run = 0;
+    T v[SP_ITEMS], run = 0;
 #pragma unroll
     for (int k = 0; k < SP_ITEMS; k++) {
       const uint32_t e = tid * SP_ITEMS + k;
-      v[k] = e < n_need ? pwr<FMT>(iq, base + e) : 0.0;
+      v[k] = e < n_need ? sp_term<FMT>(iq, base + e) : (T)0;
       run += v[k];
     }
     // block exclusive scan of the per-thread totals
-    double incl = run;
+    T incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      const T t = __shfl_up_sync(0xffffffffu, incl, o);
       if ((tid & 31) >= (uint32_t)o) incl += t;
     }
     __syncthreads();                                 // the previous half frame's prefix sums have been consumed
     if ((tid & 31) == 31) wsum[tid >> 5] = incl;
     __syncthreads();
-    double woff = 0;
+    T woff = 0;
     for (uint32_t w = 0; w < (tid >> 5); w++) woff += wsum[w];
-    double a = woff + incl - run;
+    T a = woff + incl - run;
 #pragma unroll
     for (int k = 0; k < SP_ITEMS; k++) {
       ps[tid * SP_ITEMS + k] = a;
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_fold_kernel(const void* __restr
 #pragma unroll
     for (int k = 0; k < SP_TILE / SP_THREADS; k++) {
       const uint32_t i = tid + k * SP_THREADS;
-      const double sp = (ps[i + 274] - ps[i]) / 274;
+      const double sp = ((double)(ps[i + 274] - ps[i]) * unit) / 274;
       acc[k] = m == 0 ? sp : acc[k] + sp;            // searcher.cpp:213-216: sp_incoherent = sp(0..9599) + sp(9600..) + ...
     }
   }
@@ -331,24 +347,31 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const float* __restrict__
   frq_out[((size_t)b * 3 + t) * LCS_N_FOLD + idx] = best_f;
 }
 
-// Vectorised variant for ds_comb_arm <= 4: one thread = 4 consecutive fold positions, ONE 128-bit load per hypothesis;
-// the neighbours' edge values come from the adjacent lanes (warp shuffles), only the first and the last lane of a warp
-// fetch the halo of the neighbouring warp themselves (9600 % 4 == 0 so the circular wrap is a quad index wrap).  The f
-// loop is unrolled so that several hypotheses' loads are in flight per thread.
+// x / (2*arm+1) for the box filter: q = RN(x*r); q += RN(x - n*q) * r equals the IEEE quotient for every non-negative float
+// when n is 1, 3, 5, 7 or 9 (exhaustive check, tools/divchk.c) - three instructions instead of the division sequence.
+template <int N>
+__device__ __forceinline__ float div_small_odd(float x) {
+  if (N == 1) return x;
+  constexpr float r = 1.0f / (float)N;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-(float)N, q, x), r, q);
+}
+
+// Vectorised variant for ds_comb_arm <= 4: one thread = 4 consecutive fold positions, three 128-bit loads per hypothesis
+// (previous / own / next quad; the neighbours' quads are L1 hits; 9600 % 4 == 0 so the circular wrap is a quad index
+// wrap).  HBM-bound: 5.1 TB/s in the round-2 ncu capture.
 template <int ARM>
 __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict__ single_planar, double* __restrict__ pow_out,
                                                         int32_t* __restrict__ frq_out, float* __restrict__ incoherent_planar,
                                                         const uint32_t n_f_stride, const int* __restrict__ plan_nf,
                                                         const uint32_t* __restrict__ buf_plan) {
-  constexpr uint32_t NQ = LCS_N_FOLD / 4;      // 2400 quads = 75 warps exactly
+  constexpr uint32_t NQ = LCS_N_FOLD / 4;
   const uint32_t q = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
-  if (q >= NQ) return;                          // whole warps only (2400 = 75 * 32)
-  const uint32_t lane = threadIdx.x & 31;
+  if (q >= NQ) return;
   const uint32_t n_f = (uint32_t)__ldg(plan_nf + (buf_plan ? __ldg(buf_plan + b) : 0u));
   const uint32_t qp = q == 0 ? NQ - 1 : q - 1, qn = q == NQ - 1 ? 0 : q + 1;
   const float4* s = reinterpret_cast<const float4*>(single_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD);
   float4* inc_out = incoherent_planar ? reinterpret_cast<float4*>(incoherent_planar + ((size_t)b * 3 + t) * n_f_stride * LCS_N_FOLD) : nullptr;
-  const float denom = (float)(2 * ARM + 1);
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int best_f[4] = {0, 0, 0, 0};
 #pragma unroll 4
@@ -356,26 +379,19 @@ __global__ void __launch_bounds__(128) epilogue4_kernel(const float* __restrict_
     const float4* sf = s + (size_t)f * NQ;
     const float4 c = __ldg(sf + q);
     float w[12];
-    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
     if (ARM > 0) {
-      // previous quad from lane-1, next quad from lane+1
-      float4 pv, nx;
-      pv.x = __shfl_up_sync(0xffffffffu, c.x, 1); pv.y = __shfl_up_sync(0xffffffffu, c.y, 1);
-      pv.z = __shfl_up_sync(0xffffffffu, c.z, 1); pv.w = __shfl_up_sync(0xffffffffu, c.w, 1);
-      nx.x = __shfl_down_sync(0xffffffffu, c.x, 1); nx.y = __shfl_down_sync(0xffffffffu, c.y, 1);
-      nx.z = __shfl_down_sync(0xffffffffu, c.z, 1); nx.w = __shfl_down_sync(0xffffffffu, c.w, 1);
-      if (lane == 0) pv = __ldg(sf + qp);
-      if (lane == 31) nx = __ldg(sf + qn);
+      const float4 pv = __ldg(sf + qp), nx = __ldg(sf + qn);
       w[0] = pv.x; w[1] = pv.y; w[2] = pv.z; w[3] = pv.w;
       w[8] = nx.x; w[9] = nx.y; w[10] = nx.z; w[11] = nx.w;
     }
+    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
     float v[4];
 #pragma unroll
     for (int o = 0; o < 4; o++) {
       float x = w[4 + o];
 #pragma unroll
       for (int a = 1; a <= ARM; a++) x = __fadd_rn(x, __fadd_rn(w[4 + o - a], w[4 + o + a]));  // searcher.cpp:336
-      x = __fdiv_rn(x, denom);                                                             // :343
+      x = div_small_odd<2 * ARM + 1>(x);                                                    // :343
       v[o] = x;
       if (f == 0 || x > best[o]) { best[o] = x; best_f[o] = (int)f; }                      // :371-377
     }

@@ -45,8 +45,8 @@
 #ifndef LCS_TC_PROFILE
 #define LCS_TC_PROFILE 0
 #endif
-#ifndef LCS_TC_LD1
-#define LCS_TC_LD1 0     // 1: all three digit planes of a part in one tcgen05.ld round (more registers live)
+#ifndef LCS_TC_EXP
+#define LCS_TC_EXP 0     // timing experiments (wrong results): 1 = no fold, 2 = drain only, 3 = no write-out, 4 = slots released unread
 #endif
 #if LCS_TC_PROFILE
 #define TC_CLK() clock64()
@@ -84,8 +84,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait parks the warp until the phase completes or the suspend-time hint (ns) expires: without a hint the hardware
-// limit is short and the epilogue warps spent ~15 % of the SM's issue slots polling (ncu r02c: SYNCS + BRA + YIELD)
+// try_wait parks the warp until the phase completes or the suspend-time hint (ns) expires (hints of 100 ns ... 20 us
+// measured identical: the polling seen in ncu r02c does not cost kernel time)
 #ifndef LCS_TC_WAIT_HINT_NS
 #define LCS_TC_WAIT_HINT_NS 2000
 #endif
@@ -148,7 +148,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void epi_bar(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- work distribution: runs of consecutive tiles (see the header comment) ----
 struct TcRun {
@@ -229,7 +229,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
   using SM = TcSmem<NC, NGRP, J>;
   constexpr tc::Layout LAY{NC, NGRP, J};
   constexpr int C = LAY.c(), NPAD = LAY.npad(), NJOB = LAY.njob(), NSLOT = LAY.nslot();
-  constexpr int THREADS = LAY.threads(), N_EPI_WARPS = 4 * NGRP * J;
+  constexpr int THREADS = LAY.threads(), SET_THREADS = 32 * 4 * NGRP;     // SET_THREADS: epilogue threads of one job
   static_assert(NC == 16, "one tcgen05.ld.x16 per digit plane");
   static_assert(NSLOT >= 2 && NSLOT >= J, "TMEM ring too short");
   static_assert(SM::TOTAL <= 232448, "shared memory");
@@ -431,15 +431,11 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
       t_fwait += c1 - c0;
       tc_fence_after();
       const uint32_t src = lane_base + slot * NJOB;
-#if LCS_TC_LD1
-      int a1[NC];
-      tmem_ld16(src, t);
-      tmem_ld16(src + C, a1);
-      tmem_ld16(src + 2 * C, a);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a1[c];
-#else
+#if LCS_TC_EXP == 4          // timing experiment: slots released unread (wrong results)
+      for (int c = 0; c < NC; c++) { t[c] = c; a[c] = c; }
+      if (false)
+#endif
+      {
       tmem_ld16(src, t);
       tmem_ld16(src + C, a);
       tmem_ld_wait();
@@ -447,7 +443,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
       for (int c = 0; c < NC; c++) t[c] = t[c] * 256 + a[c];
       tmem_ld16(src + 2 * C, a);
       tmem_ld_wait();
-#endif
+      }
       t_ld += TC_CLK() - c1;
       tc_fence_before();
       __syncwarp();
@@ -472,14 +468,20 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
     TcRun r;
     while (it.next(p, r)) {
       if (r.pp != cur_pp) {
-        // constants and fold offsets of the new plan / pass
-        epi_bar(32 * N_EPI_WARPS);
-        const int et = tid - 64;
+        // constants and fold offsets of the new plan / pass: every job set loads those of its own C columns
+        epi_bar(1 + job, SET_THREADS);
+        const int et = (ewarp - job * 4 * NGRP) * 32 + lane;       // thread index inside the set
         const float* gc = p.corr + (size_t)r.pp * 2 * NPAD;
         const int16_t* gd = p.dsh + (size_t)r.pp * tc::M_MAX * NPAD;
-        for (int i = et; i < 2 * NPAD; i += 32 * N_EPI_WARPS) sCorr[i] = __ldg(gc + i);
-        for (int i = et; i < (int)p.n_comb * NPAD; i += 32 * N_EPI_WARPS) sDoff[i] = -4 * (int)__ldg(gd + i);
-        epi_bar(32 * N_EPI_WARPS);
+        for (int i = et; i < 2 * C; i += SET_THREADS) {
+          const int o = (i / C) * NPAD + job * C + i % C;
+          sCorr[o] = __ldg(gc + o);
+        }
+        for (int i = et; i < (int)p.n_comb * C; i += SET_THREADS) {
+          const int o = (i / C) * NPAD + job * C + i % C;
+          sDoff[o] = -4 * (int)__ldg(gd + o);
+        }
+        epi_bar(1 + job, SET_THREADS);
         cur_pp = r.pp;
       }
       const int f0 = __ldg(&p.geo[r.pp].f0);
@@ -490,6 +492,12 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int q = 0; q < tc::NSUB; q++) {
             float x[NC], rr[NC];
+#if LCS_TC_EXP == 2 || LCS_TC_EXP == 4   // timing experiments: drain + release only (wrong results)
+            drain_part(x, cre);
+            drain_part(rr, cim);
+            if (x[0] + rr[1] == 1.2345f) sWin[0] = 1.f;
+            continue;
+#endif
             drain_part(x, cre);
 #pragma unroll
             for (int c = 0; c < NC; c++) rr[c] = __fmul_rn(x[c], x[c]);
@@ -506,6 +514,10 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
               const int4 d4 = *reinterpret_cast<const int4*>(doff + c);
               d[c] = d4.x; d[c + 1] = d4.y; d[c + 2] = d4.z; d[c + 3] = d4.w;
             }
+#if LCS_TC_EXP == 1          // timing experiment: no fold (wrong results)
+            if (rr[0] == 1.2345f) sWin[0] = rr[NC - 1];
+            continue;
+#endif
 #pragma unroll
             for (int c = 0; c < NC; c++) x[c] = *reinterpret_cast<const float*>(myWinB + d[c] + (c * tc::WSTR + q * tc::NSUBL) * 4);
 #pragma unroll
@@ -514,12 +526,15 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
         }
         // ---- tile done: the 256 oldest window positions are final -> xc_incoherent_single rows (coalesced); the HALO
         // youngest carry over to the next tile of the run ----
+        // A job set owns the window rows of its C columns exclusively, so the two sets write out independently (named
+        // barrier 1 + job): while one set is in its write-out the other keeps draining its jobs.
         long long c0 = TC_CLK();
-        epi_bar(32 * N_EPI_WARPS);
+        epi_bar(1 + job, SET_THREADS);
         const float ncf = (float)p.n_comb, rcp = p.rcp_ncomb;
         const int pb = r.p0 + (int)(tc::NT * k) - tc::HALO;       // fold position of window index 0
         const bool last = k + 1 == r.n_tiles;
-        for (uint32_t row = ewarp; row < n_templ; row += N_EPI_WARPS) {
+        const uint32_t row_end = min(n_templ, (uint32_t)((job + 1) * C));
+        for (uint32_t row = job * C + (ewarp - job * 4 * NGRP); row < (LCS_TC_EXP == 3 ? 0u : row_end); row += 4 * NGRP) {
           const uint32_t rf = row / 3, rt = row - 3 * rf;
           float* dst = p.single_planar + (((size_t)r.b * 3 + rt) * p.n_f_stride + f0 + rf) * tc::N_FOLD;
           float* src = sWin + row * tc::WSTR;
@@ -545,7 +560,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int j = tc::HALO + lane; j < tc::WSTR; j += 32) src[j] = 0.f;
         }
-        epi_bar(32 * N_EPI_WARPS);
+        epi_bar(1 + job, SET_THREADS);
         t_wout += TC_CLK() - c0;
       }
     }
