@@ -405,10 +405,14 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's log (rank / communicator lines) goes to stderr so that stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's log (version banner, communicator lines with rank / nranks) goes to stderr so that stdout stays the one
+        # JSON line; a level the environment asked for is kept if it is at least INFO
+        if rank == 0:
+            print("bench.py: NCCL env before init: %s" % {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}, file=sys.stderr)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     f = f_grid() if args.workload == "search" else np.array([0.0])      # searcher_thread.cpp:97-98: one offset
