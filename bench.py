@@ -281,6 +281,39 @@ def load_real_capture():
     return g["cu8"].reshape(-1, 2)
 
 
+def bind_to_gpu_numa(torch, local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, so that the page-locked host buffers of the e2e legs are
+    allocated in (and the copy threads run on) memory local to the GPU's PCIe root complex - what `numactl --cpunodebind`
+    does for a user.  Returns (original affinity, note); any failure leaves the affinity untouched."""
+    orig = os.sched_getaffinity(0)
+    try:
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except AttributeError:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+            bid = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+            bid = bid.decode() if isinstance(bid, bytes) else bid
+            bus = bid.lower()[-12:]                     # "00000000:9C:00.0" -> "0000:9c:00.0"
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return orig, "gpu %s: no NUMA node reported" % bus
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        use = cpus & orig
+        if not use:
+            return orig, "gpu %s: NUMA node %d has no CPU in this process' affinity mask" % (bus, node)
+        os.sched_setaffinity(0, use)
+        return orig, "gpu %s -> NUMA node %d, %d CPUs" % (bus, node, len(use))
+    except Exception as e:  # noqa
+        return orig, "not bound (%s)" % e
+
+
 def all_max(torch, dist, world, dev, v):
     t = torch.tensor([v], dtype=torch.float64, device=dev)
     if world > 1:
@@ -403,6 +436,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    orig_affinity, numa_note = bind_to_gpu_numa(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's log (version banner, communicator lines with rank / nranks) goes to stderr so that stdout stays the one
@@ -485,6 +519,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import lcs_oracle as O
+        os.sched_setaffinity(0, orig_affinity)          # the CPU oracle may use every host core
         O.set_threads(host_threads())
         r_last = (args.warmup + args.steps - 1) % ring
         b_chk = B // 2
@@ -496,6 +531,7 @@ def main():
         e_p = float(np.abs(got_p - ref["pow"]).max() / ref["pow"].max())
         e_spi = float(np.abs(d_spi[r_last][b_chk].cpu().numpy() / ref["sp_incoherent"] - 1).max())
         frq_bad = int((d_frq[r_last][b_chk].cpu().numpy() != ref["frq"]).sum())
+        bind_to_gpu_numa(torch, local)
         parity = {"buffer": "ring slot %d, buffer %d of the last timed step" % (r_last, b_chk), "rel_err_single": e_s, "rel_err_pow": e_p,
                   "rel_err_sp_incoherent": e_spi, "frq_mismatches_of_28800": frq_bad, "tolerance": 1e-6,
                   "ok": bool(e_s < 1e-6 and e_p < 1e-6 and e_spi < 1e-12 and frq_bad < 58)}
@@ -616,7 +652,9 @@ def main():
             line["sweep"] = sweep_res
         if tracker_res is not None:
             line["tracker"] = tracker_res
+        line["config"]["host_binding"] = numa_note
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, orig_affinity)
             line["cpu_baseline"] = cpu_baseline_leg(f)
         print(json.dumps(line))
     plan.close()
