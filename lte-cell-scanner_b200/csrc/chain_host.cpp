@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "chain_host.hpp"
 
@@ -412,9 +413,15 @@ void decode_mib(const lcs_cell& cell, const cd* tfg, int n_ofdm, const RsDl& rs,
   out = cell;
   const int n = rs.n_symb;
   const int n_id_cell = cell.n_id_2 + 3 * cell.n_id_1;
+  // channel estimates of the four candidate antenna ports: independent, one thread each
   std::vector<cd> ce[4];
   double npv[4];
-  for (int p = 0; p < 4; p++) chan_est(rs, tfg, n_ofdm, p, ce[p], npv[p]);
+  {
+    std::thread th[3];
+    for (int p = 1; p < 4; p++) th[p - 1] = std::thread([&, p] { chan_est(rs, tfg, n_ofdm, p, ce[p], npv[p]); });
+    chan_est(rs, tfg, n_ofdm, 0, ce[0], npv[0]);
+    for (auto& t : th) t.join();
+  }
   const int n_sym = cell.cp_type == 1 ? 960 : 864;
   const std::vector<uint8_t> scr = lte_pn((uint32_t)n_id_cell, 2 * n_sym);
   std::vector<int> pos;
@@ -422,6 +429,12 @@ void decode_mib(const lcs_cell& cell, const cd* tfg, int n_ofdm, const RsDl& rs,
   std::vector<cd> y(n_sym), h[4];
   for (auto& v : h) v.resize(n_sym);
   std::vector<double> llr(2 * n_sym);
+  // The reference tries 4 frame-timing guesses x {1, 2, 4} ports in this order and stops at the first CRC match
+  // (:1560-1640).  The soft bits of all 12 attempts are prepared first, the 12 tail-biting decodes (the expensive part) run
+  // on parallel threads, and the first attempt IN THE REFERENCE'S ORDER whose CRC matches is taken: same result.
+  struct Attempt { double d[120]; uint8_t c[40]; bool ok; int guess, n_ports; };
+  std::vector<Attempt> att;
+  att.reserve(12);
   for (int guess = 0; guess < 4; guess++) {
     // PBCH resource elements of 4 consecutive frames (:1482-1522)
     int q = 0;
@@ -463,32 +476,49 @@ void decode_mib(const lcs_cell& cell, const cd* tfg, int n_ofdm, const RsDl& rs,
           llr[2 * t + 3] = 2 * std::sqrt(2.0) * s1.imag() / np;
         }
       }
-      // descramble, undo rate matching (average the 16 repetitions), decode, CRC (:1617-1636)
-      double d[120] = {0};
+      // descramble, undo rate matching (average the 16 repetitions) (:1617-1630)
+      Attempt a;
+      a.guess = guess;
+      a.n_ports = n_ports;
+      a.ok = false;
       int cnt[120] = {0};
+      for (int i = 0; i < 120; i++) a.d[i] = 0;
       for (int k = 0; k < 2 * n_sym; k++) {
-        d[pos[k]] += scr[k] ? -llr[k] : llr[k];
+        a.d[pos[k]] += scr[k] ? -llr[k] : llr[k];
         cnt[pos[k]]++;
       }
       for (int i = 0; i < 120; i++)
-        if (cnt[i] > 1) d[i] /= cnt[i];
-      uint8_t c[40], crc[16];
-      viterbi_tailbite(d, c);
-      crc16(c, 24, crc);
-      if (n_ports == 2) for (int i = 0; i < 16; i++) crc[i] ^= 1;
-      if (n_ports == 4) for (int i = 1; i < 16; i += 2) crc[i] ^= 1;
-      if (std::memcmp(crc, c + 24, 16) != 0) continue;
-      out.n_ports = n_ports;
-      static const int bw[6] = {6, 15, 25, 50, 75, 100};
-      const int bwi = c[0] * 4 + c[1] * 2 + c[2];
-      if (bwi < 6) out.n_rb_dl = bw[bwi];
-      out.phich_duration = c[3] ? 2 : 1;
-      out.phich_resource = 1 + c[4] * 2 + c[5];
-      int sfn8 = 0;
-      for (int i = 0; i < 8; i++) sfn8 = (sfn8 << 1) | c[6 + i];
-      out.sfn = fmod_floor_i(sfn8 * 4 - guess, 1024);  // :1684-1685 (int8 wrap is a multiple of 1024 after *4)
-      return;
+        if (cnt[i] > 1) a.d[i] /= cnt[i];
+      att.push_back(a);
     }
+  }
+  auto decode = [](Attempt& a) {   // Viterbi + CRC with the port-count mask (:1631-1636)
+    uint8_t crc[16];
+    viterbi_tailbite(a.d, a.c);
+    crc16(a.c, 24, crc);
+    if (a.n_ports == 2) for (int i = 0; i < 16; i++) crc[i] ^= 1;
+    if (a.n_ports == 4) for (int i = 1; i < 16; i += 2) crc[i] ^= 1;
+    a.ok = std::memcmp(crc, a.c + 24, 16) == 0;
+  };
+  {
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < att.size(); i++) th.emplace_back([&, i] { decode(att[i]); });
+    decode(att[0]);
+    for (auto& t : th) t.join();
+  }
+  for (const Attempt& a : att) {
+    if (!a.ok) continue;
+    const uint8_t* c = a.c;
+    out.n_ports = a.n_ports;
+    static const int bw[6] = {6, 15, 25, 50, 75, 100};
+    const int bwi = c[0] * 4 + c[1] * 2 + c[2];
+    if (bwi < 6) out.n_rb_dl = bw[bwi];
+    out.phich_duration = c[3] ? 2 : 1;
+    out.phich_resource = 1 + c[4] * 2 + c[5];
+    int sfn8 = 0;
+    for (int i = 0; i < 8; i++) sfn8 = (sfn8 << 1) | c[6 + i];
+    out.sfn = fmod_floor_i(sfn8 * 4 - a.guess, 1024);  // :1684-1685 (int8 wrap is a multiple of 1024 after *4)
+    return;
   }
 }
 
