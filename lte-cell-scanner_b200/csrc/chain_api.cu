@@ -55,29 +55,39 @@ lcs_status cell_chain_dev(lcs_ctx* ctx, const void* d_cap, int fmt, uint32_t n_c
     lcs_cell c;                      // after pss_sss_foe
     std::vector<cd> tfg;
     std::vector<double> ts;
-    lcs_cell out;                    // after decode_mib
+    lcs_cell out{};                  // after decode_mib
   };
-  std::vector<Pending> pend;
-  pend.reserve(pk.size());
-  for (lcs_cell c : pk) {
-    lcs_cell o;
-    rc = dev_sss_detect(ctx, cs, d_cap, fmt, n_cap, c, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, o, nullptr);
-    if (rc == LCS_ERR_RANGE) continue;   // the reference would index outside the buffer here
-    if (rc != LCS_OK) return rc;
-    if (o.n_id_1 == -1) continue;  // CellSearch.cpp:530-534
-    c = o;
+  // device stages, each for all peaks at once
+  std::vector<lcs_cell> det;
+  std::vector<lcs_status> st1;
+  rc = dev_sss_detect_batch(ctx, cs, d_cap, fmt, n_cap, pk, THRESH2_N_SIGMA, fc_req, fc_prog, fs_prog, det, st1, nullptr);
+  if (rc != LCS_OK) return rc;
+  std::vector<lcs_cell> surv;
+  for (size_t i = 0; i < pk.size(); i++) {
+    if (st1[i] == LCS_ERR_RANGE) continue;   // the reference would index outside the buffer here
+    if (det[i].n_id_1 == -1) continue;       // CellSearch.cpp:530-534
     // searcher_thread.cpp:153-174: cells that are being tracked are not examined further
     bool already_tracked = false;
-    for (uint32_t k = 0; k < n_tracked; k++) already_tracked |= tracked[k] == c.n_id_2 + 3 * c.n_id_1;
+    for (uint32_t k = 0; k < n_tracked; k++) already_tracked |= tracked[k] == det[i].n_id_2 + 3 * det[i].n_id_1;
     if (already_tracked) continue;
-    rc = dev_pss_sss_foe(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, o);
-    if (rc != LCS_OK) return rc;
-    c = o;
+    surv.push_back(det[i]);
+  }
+  std::vector<lcs_cell> foe;
+  rc = dev_pss_sss_foe_batch(ctx, cs, d_cap, fmt, n_cap, surv, fc_req, fc_prog, fs_prog, foe);
+  if (rc != LCS_OK) return rc;
+  std::vector<std::vector<cd>> tfgs;
+  std::vector<std::vector<double>> tss;
+  std::vector<lcs_status> st3;
+  rc = dev_extract_tfg_batch(ctx, cs, d_cap, fmt, n_cap, foe, fc_req, fc_prog, fs_prog, tfgs, tss, st3);
+  if (rc != LCS_OK) return rc;
+  std::vector<Pending> pend;
+  pend.reserve(foe.size());
+  for (size_t i = 0; i < foe.size(); i++) {
+    if (st3[i] == LCS_ERR_RANGE) continue;
     Pending q;
-    rc = dev_extract_tfg(ctx, cs, d_cap, fmt, n_cap, c, fc_req, fc_prog, fs_prog, q.tfg, q.ts);
-    if (rc == LCS_ERR_RANGE) continue;
-    if (rc != LCS_OK) return rc;
-    q.c = c;
+    q.c = foe[i];
+    q.tfg.swap(tfgs[i]);
+    q.ts.swap(tss[i]);
     pend.push_back(std::move(q));
   }
   auto host_stage = [&](Pending& q) {
