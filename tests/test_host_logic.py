@@ -218,3 +218,61 @@ def test_tc_integer_formulation_numpy(oracle):
                 got = complex(v_re, v_im) / (S * 128)
                 worst = max(worst, abs(got - ref[t, L, fi]) / np.abs(ref[t, :, fi]).max())
     assert worst < 3e-7, worst            # float32 rounding of the reference's stored xc + 2^-24 template quantisation
+
+
+def test_tc_run_decomposition_covers_every_position_once():
+    """The tcgen05 correlator distributes work in tile space (xcorr_tc.cu: launch_xcorr_fold_tc / TcRunIter): CTA i takes
+    tiles [i*t_cta, (i+1)*t_cta) of the sequence [unit][tu]; a run of T tiles yields 256*T - 32 fold positions.  Restated
+    here: for many (units, SMs) every position 0..9599 of every unit is produced by exactly one run, and no run needs more
+    tiles than it was given."""
+    NT, HALO, NF = 256, 32, 9600
+
+    def plan(n_units, n_sm):
+        tu = (NF + HALO + NT - 1) // NT
+        while True:
+            t_cta = (n_units * tu + n_sm - 1) // n_sm
+            runs = (tu + t_cta - 1) // t_cta + 1
+            if NT * tu - HALO * runs >= NF:
+                return tu, t_cta
+            tu += 1
+
+    for n_units, n_sm in [(1, 148), (2, 148), (3, 7), (8, 148), (32, 148), (64, 148), (128, 148), (384, 148), (768, 148), (5, 1), (37, 13)]:
+        tu, t_cta = plan(n_units, n_sm)
+        total = n_units * tu
+        cover = np.zeros((n_units, NF), np.int32)
+        grid = (total + t_cta - 1) // t_cta
+        assert grid <= max(n_sm, 1) or t_cta == 1
+        for cta in range(grid):
+            t, t_end = cta * t_cta, min((cta + 1) * t_cta, total)
+            while t < t_end:
+                u = t // tu
+                base = u * tu
+                a = t - base
+                e = min(t_end, base + tu)
+                bb = e - base
+                nb = (base + a) // t_cta - base // t_cta
+                t = e
+                p0 = NT * a - HALO * nb
+                if p0 >= NF:
+                    continue
+                p1 = min(NT * bb - HALO * (nb + 1), NF)
+                assert p1 > p0
+                n_tiles = min(bb - a, (p1 - p0 + HALO + NT - 1) // NT)
+                assert NT * n_tiles - HALO >= p1 - p0          # the run's tiles suffice for its positions
+                cover[u, p0:p1] += 1
+        assert (cover == 1).all(), (n_units, n_sm, tu, t_cta)
+
+
+def test_three_instruction_division_matches_ieee_on_samples():
+    """q = RN(x*r); q += RN(x - n*q) * r with r = RN(1/n) is used instead of x / n for n = n_comb (15) and 2*arm+1 (3, 5, 7, 9).
+    tools/divchk.c proves equality for EVERY non-negative float; here a sampled re-check in float32 arithmetic."""
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.random(200000, np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 200000).astype(np.float32),
+                        np.array([0.0, 1e-45, 1.1754944e-38, 3.4028235e38], np.float32)]).astype(np.float32)
+    for n in (3, 5, 7, 9, 15):
+        d = np.float32(n)
+        r = np.float32(1.0) / d
+        q = (x * r).astype(np.float32)
+        e = (x.astype(np.float64) - d.astype(np.float64) * q.astype(np.float64)).astype(np.float32)   # fma(-n, q, x): exact product, one rounding
+        q2 = (e.astype(np.float64) * r.astype(np.float64) + q.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(q2, (x / d).astype(np.float32)), n
