@@ -523,6 +523,10 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int c = 0; c < NC; c++) *reinterpret_cast<float*>(myWinB + d[c] + (c * tc::WSTR + q * tc::NSUBL) * 4) = __fadd_rn(x[c], rr[c]);
           }
+          // The four lane-quarter warps of a column group fold into the same window rows; a lag of one quarter at this
+          // half frame and a lag of its neighbour at the next one (different fold offset) can hit the same window index.
+          // The MMA pipeline keeps them a job apart in practice; this 128-thread barrier makes the ordering a guarantee.
+          epi_bar(3 + cell, 128);
         }
         // ---- tile done: the 256 oldest window positions are final -> xc_incoherent_single rows (coalesced); the HALO
         // youngest carry over to the next tile of the run ----

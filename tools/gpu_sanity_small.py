@@ -22,5 +22,15 @@ g = np.load(os.path.join(ROOT, "tests/golden/capbuf_0000.npz"))
 real = g["cu8"].reshape(-1, 2)
 new = ctx.tracker_search_cu8(real, 35000.0, 739e6, 739e6, 1.92e6, 0.0)
 print("tracker cells", [c.n_id_cell() for c, _ in new])
+# multi-plan paths: frequency sweep (one plan per channel, tensor-core correlator) and multi-channel tracker search (FP32, n_f = 1)
+sw = L.Sweep(ctx, 29000)
+iq = np.stack([synth(29000) for _ in range(5)])
+fcs = 739e6 + 100e3 * np.arange(5)
+res = sw.search_cu8(iq, fcs, np.arange(-17, 18) * 5000.0)
+trk = sw.track_cu8(iq, [100.0, -2000.0, 0.0, 35000.0, 5.0], fcs, late=[0.0] * 5, tracked=[[], [1], [], [], [2, 3]])
+print("sweep cells %s tracker cells %s" % ([len(c) for c in res], [len(c) for c in trk]))
+sw.close()
+best, resid, n = ctx.kalibrate_cu8(synth(29000), 739e6, 739e6, 1.92e6, 120.0)
+print("kalibrate on noise: %d cells" % n)
 ctx.close()
-print("done")
+print("sanity ok")

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU frequency sweep demo (BASELINE config 4 in miniature): N ranks, channels round-robin, each rank
-runs the whole CellSearch chain per channel on its own B200, NCCL all_gather of the cell records, dedup on rank 0.
+runs its channels through lcs_sweep_search_cu8 on its own B200, NCCL all_gather of the cell records, dedup on rank 0.
 Channel 739.0 MHz carries the reference's real capture (tests/golden/capbuf_0000.npz); the others are synthetic noise.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sweep_demo.py [n_channels]
 """
@@ -40,16 +40,19 @@ def main():
             cap = np.clip(np.round(127.5 + 20 * rng.standard_normal((153600, 2))), 0, 255).astype(np.uint8)
         chans.append((i, fc, cap))
     ctx = L.Context(local)
+    sw = L.Sweep(ctx, 153600)
+    f = L.f_search_set(fc0, 120.0)                       # CellSearch.cpp:463-464: one grid for the sweep, from freq_start
+    fcs = [c[1] for c in chans]
+    mine = sweep.shard(n_ch, rank, world)
+    iq = np.stack([chans[i][2] for i in mine]) if mine else np.zeros((0, 153600, 2), np.uint8)
 
-    def search(fc, cap):
-        cells, _ = ctx.cell_search(cap, L.f_search_set(fc, 120.0), fc, fc, 1.92e6)
-        return cells
+    def run():
+        return sweep.sweep_batched(fcs, iq, lambda b, fc: sw.search_cu8(b, fc, f), L.new_cell, L.dedup, dist=d, device=dev)
 
-    search(chans[0][1], chans[0][2])            # warm-up (plan build, context)
-    search(739e6, real)                         # ... and the per-peak kernels (first-use module load)
+    run()                                       # warm-up (allocations, module load)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = sweep.sweep(chans, search, L.new_cell, L.dedup, dist=d, device=dev)
+    res = run()
     dt = time.perf_counter() - t0
     if rank == 0:
         print("sweep of %d channels on %d GPU(s): %.3f s (%.1f channels/s), %d cell(s)" % (n_ch, world, dt, n_ch / dt, len(res)))
