@@ -243,10 +243,8 @@ lcs_status planset_build(lcs_ctx* ctx, PlanSet& ps, uint32_t n_cap, uint8_t arm,
     LCS_CUDA(ctx, cudaMemsetAsync(ps.d_corr.p, 0, (size_t)P * n_pass * 2 * npad * 4, st));
   }
   LCS_CUDA(ctx, cudaEventRecord(ps.staged, st));
-  if (!ps.d_flag.p) {
-    LCS_CUDA(ctx, ps.d_flag.alloc(1));
-    LCS_CUDA(ctx, cudaMemsetAsync(ps.d_flag.p, 0, 4, st));
-  }
+  if (!ps.d_flag.p) LCS_CUDA(ctx, ps.d_flag.alloc(1));
+  LCS_CUDA(ctx, cudaMemsetAsync(ps.d_flag.p, 0, 4, st));         // diagnostics of THIS build
   if (want_fp32) {
     LCS_CUDA(ctx, ps.d_w01.ensure((size_t)P * n_f_stride * XC_NTAP_PAD));
     LCS_CUDA(ctx, ps.d_w2.ensure((size_t)P * n_f_stride * XC_NTAP_PAD));

@@ -582,3 +582,41 @@ def test_cellsearch_cli_batched_sweep(ctx, tmp_path, capbuf0000):
         assert len(rows) == 2
         outs.append(rows)
     assert outs[0] == outs[1]
+
+
+def test_dropin_routes_8bit_exact_input_to_the_tensor_core_kernel(ctx, lcs, capbuf0000):
+    """lcs_xcorr_pss takes the IT++ c128 vector; a capture that holds exactly (u8-127)/128 (capbuf.cpp:172-175) must be
+    served by the tcgen05 correlator: its `single` is bit-identical to an explicit tensor-core plan on the raw bytes,
+    while the same samples scaled by 0.999 (no longer 8-bit exact) take the FP32 correlator and differ in the last bits."""
+    fc = capbuf0000["fc"]
+    f = lcs.f_search_set(fc, 120.0)
+    out = ctx.xcorr_pss(capbuf0000["capbuf"], f, 2, fc, fc, 1.92e6, want_incoherent=False)
+    plan = ctx.plan(capbuf0000["cu8"].shape[0], f, 2, fc, fc, 1.92e6, max_batch=1, kernel=lcs.KERNEL_TC)
+    tc = plan.run_host_np(capbuf0000["cu8"][None], lcs.IQ_CU8)
+    plan.close()
+    assert np.array_equal(out["single"], tc["single"][0].transpose(0, 2, 1))
+    assert np.array_equal(out["pow"], tc["pow"][0]) and np.array_equal(out["frq"], tc["frq"][0])
+    scaled = ctx.xcorr_pss(capbuf0000["capbuf"] * 0.999, f, 2, fc, fc, 1.92e6, want_incoherent=False)
+    ratio = scaled["single"] / (out["single"] * 0.999 ** 2)
+    assert not np.array_equal(scaled["single"], out["single"]) and np.abs(ratio - 1).max() < 1e-4
+
+
+def test_sweep_on_a_grid_the_tensor_core_tiling_cannot_hold(ctx, lcs, oracle, capbuf0000):
+    """A sweep whose frequency grid is too sparse for the tensor-core tiling (fold-offset spread > 32 samples) falls back
+    to the FP32 correlator with per-channel templates; cells still equal the oracle's per channel."""
+    f = np.arange(-8, 9) * 35000.0
+    real, noise = capbuf0000["cu8"], synth_cu8(0xABCD)
+    fcs = np.array([739e6, 739.1e6, 745e6])
+    iq = np.stack([real, noise, real])
+    sw = lcs.Sweep(ctx, real.shape[0])
+    got = sw.search_cu8(iq, fcs, f)
+    for i, fc in enumerate(fcs):
+        cap = capbuf0000["capbuf"] if i != 1 else cu8_to_c128(noise)
+        o_cells, _ = oracle.cell_search_one(cap, f, fc, fc, 1.92e6)
+        assert [c.n_id_cell() for c in got[i]] == [c.n_id_cell() for c in o_cells], i
+        for a, b in zip(got[i], o_cells):
+            for k in ("n_id_1", "n_id_2", "cp_type", "ind", "n_ports", "n_rb_dl", "sfn"):
+                assert getattr(a, k) == getattr(b, k), (i, k)
+            assert abs(a.freq_superfine - b.freq_superfine) < 1e-6
+    assert len(got[0]) >= 1 and got[1] == []
+    sw.close()
