@@ -193,7 +193,7 @@ lcs_status lcs_kalibrate_cu8(lcs_ctx* ctx, const uint8_t* capbuf_cu8, uint32_t n
  * capture buffers, everything on the device: only the PSS peaks return.  iq_host is [batch][n_cap] in iq_format;
  * peaks is [batch][max_peaks] (fc_requested, fc_programmed, pss_pow, ind, freq, n_id_2 filled as by peak_search,
  * in the reference's order), n_peaks[batch] the number found per buffer (may exceed max_peaks: list truncated).
- * Chunks of up to 32 buffers are double-buffered over the plan's two streams. */
+ * Chunks of up to 64 buffers are double-buffered over the plan's two streams. */
 lcs_status lcs_xcorr_peaks_batch_host(lcs_xcorr_plan* plan, const void* iq_host, int iq_format, uint32_t batch,
                                       lcs_cell* peaks, uint32_t max_peaks, uint32_t* n_peaks);
 /* The whole chain of CellSearch.cpp:497-558 for every buffer of a batch of raw rtl-sdr byte buffers (cu8

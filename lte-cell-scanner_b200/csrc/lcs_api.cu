@@ -263,9 +263,9 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
   const size_t samp_bytes = iq_format == LCS_IQ_CU8 ? 2 : (iq_format == LCS_IQ_CF32 ? 8 : (iq_format == LCS_IQ_C128 ? 16 : 0));
   if (!samp_bytes) return fail(ctx, LCS_ERR_ARG, "xcorr_pss_batch_host: bad iq_format");
   LCS_CUDA(ctx, cudaSetDevice(ctx->device));
-  // chunk: large enough that the persistent correlator CTAs get several tiles each (32 buffers = 8 tiles per CTA), small
-  // enough that the copies of neighbouring chunks overlap the kernels
-  const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, 32u), batch);
+  // chunk: large enough that the persistent correlator CTAs get many tiles each (64 buffers x 38 tiles = 16.4 tiles per
+  // CTA, 3 % rounding loss), small enough that the copies of neighbouring chunks overlap the kernels
+  const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, 64u), batch);
   const size_t n_single = (size_t)3 * g.n_f_stride * LCS_N_FOLD;
   for (int s = 0; s < 2; s++) {
     LCS_CUDA(ctx, p->hb[s].iq.ensure((size_t)chunk * g.n_cap * samp_bytes + 16));

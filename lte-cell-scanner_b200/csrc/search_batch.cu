@@ -129,7 +129,7 @@ static lcs_status launch_peak_search(lcs_ctx* ctx, const XcorrGeom& g, uint32_t 
 }
 
 constexpr int SEARCH_MAX_PEAKS = 32;
-constexpr uint32_t SEARCH_CHUNK = 32;
+constexpr uint32_t SEARCH_CHUNK = 64;
 
 // Shared driver: xcorr_pss + threshold + peak_search for `batch` host capture buffers in chunks that alternate between the
 // context's two streams; `per_buffer(buffer index, device pointer of the buffer's IQ bytes, its PSS peaks)` runs on the

@@ -263,14 +263,28 @@ __global__ void __launch_bounds__(SP_THREADS) sp_fold_kernel(const void* __restr
   const uint32_t n_need = n_pos + 273;               // samples this block touches per half frame (all < n_cap)
   const double unit = FMT == LCS_IQ_CU8 ? 1.0 / 16384.0 : 1.0;
   double acc[SP_TILE / SP_THREADS];
+  // the loads of half frame m+1 are issued before the scan of half frame m (the scan's barriers would otherwise expose the
+  // full global-memory latency fifteen times per block)
+  T nxt[SP_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SP_ITEMS; k++) {
+    const uint32_t e = tid * SP_ITEMS + k;
+    nxt[k] = e < n_need ? sp_term<FMT>(iq, (size_t)b * n_cap + i_base + e) : (T)0;
+  }
   for (uint32_t m = 0; m < n_comb_sp; m++) {
-    const size_t base = (size_t)b * n_cap + (size_t)m * LCS_N_FOLD + i_base;
     T v[SP_ITEMS], run = 0;
 #pragma unroll
     for (int k = 0; k < SP_ITEMS; k++) {
-      const uint32_t e = tid * SP_ITEMS + k;
-      v[k] = e < n_need ? sp_term<FMT>(iq, base + e) : (T)0;
+      v[k] = nxt[k];
       run += v[k];
+    }
+    if (m + 1 < n_comb_sp) {
+      const size_t base = (size_t)b * n_cap + (size_t)(m + 1) * LCS_N_FOLD + i_base;
+#pragma unroll
+      for (int k = 0; k < SP_ITEMS; k++) {
+        const uint32_t e = tid * SP_ITEMS + k;
+        nxt[k] = e < n_need ? sp_term<FMT>(iq, base + e) : (T)0;
+      }
     }
     // block exclusive scan of the per-thread totals
     T incl = run;
