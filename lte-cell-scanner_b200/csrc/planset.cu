@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(160) plan_build_kernel(const double* __restric
 
 static tc::Layout pick_layout(uint32_t n_f, uint32_t& n_pass) {
   n_pass = 1;
+  if (n_f <= 5) return tc::Layout{16, 1, 1};       // tracker shape (one offset): N = 48, four epilogue warps
   if (n_f <= 16) return tc::Layout{16, 3, 1};
   if (n_f <= 21) return tc::Layout{16, 4, 1};
   if (n_f <= 32) return tc::Layout{16, 3, 2};
@@ -264,9 +265,9 @@ lcs_status planset_build(lcs_ctx* ctx, PlanSet& ps, uint32_t n_cap, uint8_t arm,
 int planset_resolve_kernel(const PlanSet& ps, int kernel, int iq_format) {
   if (kernel == LCS_KERNEL_FP32) return LCS_KERNEL_FP32;
   if (kernel == LCS_KERNEL_TC) return LCS_KERNEL_TC;
-  // AUTO: the tensor-core kernel is exact only for 8-bit IQ; its cost is flat in n_f up to a full pass while the FP32
-  // kernel's is proportional to n_f, so tiny grids (tracker mode, n_f = 1) stay on FP32.
-  return (iq_format == LCS_IQ_CU8 && ps.tc_ready && ps.geom.n_f_stride >= 4) ? LCS_KERNEL_TC : LCS_KERNEL_FP32;
+  // AUTO: the tensor-core kernel is exact only for 8-bit IQ; for that format it is the faster one at every grid size
+  // (even the single-offset tracker shape: one N = 48 job per part, ~6 us per buffer against 11 us on the FP32 cores).
+  return (iq_format == LCS_IQ_CU8 && ps.tc_ready) ? LCS_KERNEL_TC : LCS_KERNEL_FP32;
 }
 
 lcs_status planset_run(PlanSet& ps, int kernel, const void* d_iq, int iq_format, uint32_t batch, const uint32_t* d_buf_plan,

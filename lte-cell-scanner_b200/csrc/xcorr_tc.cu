@@ -589,6 +589,7 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
 // Host side
 // =============================================================================================
 lcs_status tc_init(lcs_ctx* ctx) {
+  LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16, 1, 1>::TOTAL));
   LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16, 3, 1>::TOTAL));
   LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16, 4, 1>::TOTAL));
   LCS_CUDA(ctx, cudaFuncSetAttribute(xcorr_fold_tc_kernel<16, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<16, 3, 2>::TOTAL));
@@ -657,7 +658,8 @@ int launch_xcorr_fold_tc(PlanSet& ps, const void* d_iq_cu8, uint32_t batch, cons
   q.n_tiles_total = n_units * tu;
   const uint32_t grid = (q.n_tiles_total + t_cta - 1) / t_cta;
   const tc::Layout& L = ps.lay;
-  if (L.ngrp == 3 && L.j == 1) xcorr_fold_tc_kernel<16, 3, 1><<<grid, L.threads(), TcSmem<16, 3, 1>::TOTAL, st>>>(q);
+  if (L.ngrp == 1 && L.j == 1) xcorr_fold_tc_kernel<16, 1, 1><<<grid, L.threads(), TcSmem<16, 1, 1>::TOTAL, st>>>(q);
+  else if (L.ngrp == 3 && L.j == 1) xcorr_fold_tc_kernel<16, 3, 1><<<grid, L.threads(), TcSmem<16, 3, 1>::TOTAL, st>>>(q);
   else if (L.ngrp == 4 && L.j == 1) xcorr_fold_tc_kernel<16, 4, 1><<<grid, L.threads(), TcSmem<16, 4, 1>::TOTAL, st>>>(q);
   else xcorr_fold_tc_kernel<16, 3, 2><<<grid, L.threads(), TcSmem<16, 3, 2>::TOTAL, st>>>(q);
   return 1;
