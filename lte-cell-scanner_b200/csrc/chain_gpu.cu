@@ -328,7 +328,7 @@ static lcs_status run_psss(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, in
 lcs_status dev_sss_detect_batch(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, int fmt, uint32_t n_cap,
                                 const std::vector<lcs_cell>& cells, double thresh2_n_sigma, double fc_req, double fc_prog,
                                 double fs_prog, std::vector<lcs_cell>& out, std::vector<lcs_status>& status, SssDebugHost* dbg) {
-  cudaStream_t st = ctx->streams[0];
+  cudaStream_t st = ctx->chain_stream ? ctx->chain_stream : ctx->streams[0];
   const size_t P = cells.size();
   out.assign(cells.begin(), cells.end());
   status.assign(P, LCS_OK);
@@ -441,7 +441,7 @@ lcs_status dev_sss_detect(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, int
 lcs_status dev_pss_sss_foe_batch(lcs_ctx* ctx, ChainScratch& cs, const void* d_cap, int fmt, uint32_t n_cap,
                                  const std::vector<lcs_cell>& cells, double fc_req, double fc_prog, double fs_prog,
                                  std::vector<lcs_cell>& out) {
-  cudaStream_t st = ctx->streams[0];
+  cudaStream_t st = ctx->chain_stream ? ctx->chain_stream : ctx->streams[0];
   const size_t P = cells.size();
   out.assign(cells.begin(), cells.end());
   if (P == 0) return LCS_OK;
@@ -542,7 +542,7 @@ lcs_status dev_extract_tfg_batch(lcs_ctx* ctx, ChainScratch& cs, const void* d_c
                                  const std::vector<lcs_cell>& cells, double fc_req, double fc_prog, double fs_prog,
                                  std::vector<std::vector<cd>>& tfg, std::vector<std::vector<double>>& ts,
                                  std::vector<lcs_status>& status) {
-  cudaStream_t st = ctx->streams[0];
+  cudaStream_t st = ctx->chain_stream ? ctx->chain_stream : ctx->streams[0];
   const size_t P = cells.size();
   tfg.assign(P, std::vector<cd>());
   ts.assign(P, std::vector<double>());

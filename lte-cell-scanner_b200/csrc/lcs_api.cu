@@ -129,7 +129,7 @@ lcs_status lcs_ctx_create(int device, lcs_ctx** out) {
   std::unique_ptr<lcs_ctx> c(new lcs_ctx());
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < lcs_ctx::N_STREAMS; i++)
     if (cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
       for (int k = 0; k < i; k++) cudaStreamDestroy(c->streams[k]);
       return fail(nullptr, LCS_ERR_CUDA, "stream creation failed");
@@ -149,13 +149,13 @@ lcs_status lcs_ctx_create(int device, lcs_ctx** out) {
   c->tc_scale = std::ldexp(1.0, ex);
   if (c->d_pss_td.alloc(3 * 137 * 2) != cudaSuccess ||
       cudaMemcpy(c->d_pss_td.p, &td[0][0], sizeof(td), cudaMemcpyHostToDevice) != cudaSuccess) {
-    for (int i = 0; i < 2; i++) cudaStreamDestroy(c->streams[i]);
+    for (int i = 0; i < lcs_ctx::N_STREAMS; i++) cudaStreamDestroy(c->streams[i]);
     return fail(nullptr, LCS_ERR_CUDA, "pss_td upload failed");
   }
   xcorr_fp32_init();
   lcs_status rc = tc_init(c.get());
   if (rc != LCS_OK) {
-    for (int i = 0; i < 2; i++) cudaStreamDestroy(c->streams[i]);
+    for (int i = 0; i < lcs_ctx::N_STREAMS; i++) cudaStreamDestroy(c->streams[i]);
     return rc;
   }
   *out = c.release();
@@ -169,7 +169,7 @@ void lcs_ctx_destroy(lcs_ctx* ctx) {
   for (auto* p : ctx->cached_plans) lcs_xcorr_plan_destroy(p);
   ctx->cached_plans.clear();
   chain_scratch_release(ctx);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < lcs_ctx::N_STREAMS; i++)
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
   delete ctx;
 }
@@ -251,8 +251,9 @@ lcs_status lcs_xcorr_pss_device(lcs_xcorr_plan* plan, const void* d_iq, int iq_f
                     (cudaStream_t)stream);
 }
 
-// Host-buffer batched call: chunks of the batch alternate between the context's two streams so
-// that H2D(i+1) and D2H(i-1) overlap the kernels of chunk i.
+// Host-buffer batched call: chunks of the batch rotate over the context's three streams so that the
+// copies of the neighbouring chunks overlap the kernels of chunk i (with two streams the upload of chunk
+// i+2 sits behind the download of chunk i on the same stream and only just fits behind one chunk's kernels).
 lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_format, uint32_t batch,
                                     float* h_single, double* h_pow, int32_t* h_frq, double* h_spi) {
   if (!p) return fail(nullptr, LCS_ERR_ARG, "xcorr_pss_batch_host: null plan");
@@ -267,7 +268,8 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
   // CTA, 3 % rounding loss), small enough that the copies of neighbouring chunks overlap the kernels
   const uint32_t chunk = std::min<uint32_t>(std::min<uint32_t>(p->max_batch, 64u), batch);
   const size_t n_single = (size_t)3 * g.n_f_stride * LCS_N_FOLD;
-  for (int s = 0; s < 2; s++) {
+  constexpr int NS = lcs_ctx::N_STREAMS;
+  for (int s = 0; s < NS; s++) {
     LCS_CUDA(ctx, p->hb[s].iq.ensure((size_t)chunk * g.n_cap * samp_bytes + 16));
     LCS_CUDA(ctx, p->hb[s].single.ensure(chunk * n_single));
     LCS_CUDA(ctx, p->hb[s].pow.ensure((size_t)chunk * 3 * LCS_N_FOLD));
@@ -275,7 +277,7 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
     LCS_CUDA(ctx, p->hb[s].spi.ensure((size_t)chunk * LCS_N_FOLD));
   }
   int s = 0;
-  for (uint32_t b0 = 0; b0 < batch; b0 += chunk, s ^= 1) {
+  for (uint32_t b0 = 0; b0 < batch; b0 += chunk, s = (s + 1) % NS) {
     const uint32_t nb = std::min(chunk, batch - b0);
     cudaStream_t st = ctx->streams[s];
     auto& hb = p->hb[s];
@@ -289,8 +291,7 @@ lcs_status lcs_xcorr_pss_batch_host(lcs_xcorr_plan* p, const void* h_iq, int iq_
     LCS_CUDA(ctx, cudaMemcpyAsync(h_frq + (size_t)b0 * 3 * LCS_N_FOLD, hb.frq.p, (size_t)nb * 3 * LCS_N_FOLD * 4, cudaMemcpyDeviceToHost, st));
     LCS_CUDA(ctx, cudaMemcpyAsync(h_spi + (size_t)b0 * LCS_N_FOLD, hb.spi.p, (size_t)nb * LCS_N_FOLD * 8, cudaMemcpyDeviceToHost, st));
   }
-  LCS_CUDA(ctx, cudaStreamSynchronize(ctx->streams[0]));
-  LCS_CUDA(ctx, cudaStreamSynchronize(ctx->streams[1]));
+  for (int i = 0; i < NS; i++) LCS_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
   return LCS_OK;
 }
 

@@ -90,7 +90,9 @@ struct lcs_xcorr_plan;
 struct lcs_ctx {
   int device = 0;
   int n_sm = 0;
-  cudaStream_t streams[2] = {nullptr, nullptr};
+  static constexpr int N_STREAMS = 3;           // chunks of the host-batch calls rotate over these
+  cudaStream_t streams[N_STREAMS] = {nullptr, nullptr, nullptr};
+  cudaStream_t chain_stream = nullptr;         // stream of the per-peak stages (NULL: streams[0]); the chunked search sets it to the idle stream of the chunk it examines
   std::string last_error;
   uint64_t launches = 0;
   std::vector<lcs_xcorr_plan*> cached_plans;   // for the plan-less drop-in calls
@@ -130,7 +132,7 @@ struct lcs_xcorr_plan {
     lcs::DevBuf<int32_t> npeaks;
     lcs::PinBuf<unsigned char> h_peaks;   // page-locked landing zones of the peak lists
     lcs::PinBuf<int32_t> h_npeaks;
-  } hb[2];
+  } hb[lcs_ctx::N_STREAMS];
 };
 
 namespace lcs {

@@ -137,7 +137,7 @@ constexpr uint32_t SEARCH_CHUNK = 64;
 // d_buf_plan == NULL: every buffer is searched with plan 0 of `ps`; otherwise buffer b uses plan d_buf_plan[b] and
 // h_buf_plan[b] names the same plan on the host.
 template <class F>
-static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr_plan::HostBatchBufs (&hbs)[2], const void* h_iq,
+static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr_plan::HostBatchBufs (&hbs)[lcs_ctx::N_STREAMS], const void* h_iq,
                                 int iq_format, uint32_t batch, uint32_t chunk, const uint32_t* d_buf_plan, const uint32_t* h_buf_plan,
                                 F&& per_buffer) {
   const XcorrGeom& g = ps.geom;
@@ -148,7 +148,8 @@ static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr
   chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, batch));
   const size_t n_single = (size_t)3 * g.n_f_stride * LCS_N_FOLD;
   // 16-byte aligned buffer stride inside a chunk is not required (the correlator aligns absolute addresses), only the base
-  for (int s = 0; s < 2; s++) {
+  constexpr int NS = lcs_ctx::N_STREAMS;
+  for (int s = 0; s < NS; s++) {
     auto& hb = hbs[s];
     LCS_CUDA(ctx, hb.iq.ensure((size_t)chunk * g.n_cap * samp_bytes + 16));
     LCS_CUDA(ctx, hb.single.ensure(chunk * n_single));
@@ -163,8 +164,12 @@ static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr
     LCS_CUDA(ctx, hb.h_peaks.ensure((size_t)chunk * SEARCH_MAX_PEAKS * sizeof(DevPeak)));
     LCS_CUDA(ctx, hb.h_npeaks.ensure(chunk));
   }
-  const DevPeak* h_peaks[2] = {reinterpret_cast<const DevPeak*>(hbs[0].h_peaks.p), reinterpret_cast<const DevPeak*>(hbs[1].h_peaks.p)};
-  const int32_t* h_np[2] = {hbs[0].h_npeaks.p, hbs[1].h_npeaks.p};
+  const DevPeak* h_peaks[NS];
+  const int32_t* h_np[NS];
+  for (int s = 0; s < NS; s++) {
+    h_peaks[s] = reinterpret_cast<const DevPeak*>(hbs[s].h_peaks.p);
+    h_np[s] = hbs[s].h_npeaks.p;
+  }
   auto issue = [&](uint32_t b0, int s) -> lcs_status {
     const uint32_t nb = std::min(chunk, batch - b0);
     cudaStream_t st = ctx->streams[s];
@@ -215,25 +220,28 @@ static lcs_status search_chunks(lcs_ctx* ctx, PlanSet& ps, int kernel, lcs_xcorr
           pk.push_back(c);
         }
       }
+      ctx->chain_stream = ctx->streams[s];        // this chunk's stream is idle now: the per-peak kernels do not queue behind later chunks
       lcs_status rc = per_buffer(b0 + i, (const void*)(hb.iq.p + (size_t)i * g.n_cap * samp_bytes), pk);
+      ctx->chain_stream = nullptr;
       if (rc != LCS_OK) return rc;
     }
     return LCS_OK;
   };
-  int s = 0;
-  uint32_t prev_b0 = 0;
-  bool have_prev = false;
-  for (uint32_t b0 = 0; b0 < batch; b0 += chunk, s ^= 1) {
-    lcs_status rc = issue(b0, s);
-    if (rc != LCS_OK) return rc;
-    if (have_prev) {
-      rc = finish(prev_b0, s ^ 1);
+  // chunk k runs on stream k % NS; after issuing chunk k the host finishes chunk k - (NS - 1), so NS - 1 chunks are in
+  // flight on the GPU while the oldest one's peaks are examined, and a stream's buffers are free again when it is reused
+  const uint32_t n_chunks = (batch + chunk - 1) / chunk;
+  for (uint32_t k = 0; k < n_chunks + (NS - 1); k++) {
+    if (k < n_chunks) {
+      lcs_status rc = issue(k * chunk, (int)(k % NS));
       if (rc != LCS_OK) return rc;
     }
-    prev_b0 = b0;
-    have_prev = true;
+    if (k >= (uint32_t)(NS - 1)) {
+      const uint32_t kf = k - (NS - 1);
+      lcs_status rc = finish(kf * chunk, (int)(kf % NS));
+      if (rc != LCS_OK) return rc;
+    }
   }
-  return finish(prev_b0, s ^ 1);
+  return LCS_OK;
 }
 
 }  // namespace lcs
@@ -246,7 +254,7 @@ struct lcs_sweep {
   lcs_ctx* ctx = nullptr;
   uint32_t n_cap = 0;
   PlanSet ps;
-  lcs_xcorr_plan::HostBatchBufs hb[2];
+  lcs_xcorr_plan::HostBatchBufs hb[lcs_ctx::N_STREAMS];
   DevBuf<uint32_t> d_ident;              // 0, 1, 2, ...: plan of buffer b is b
   std::vector<uint32_t> h_ident;
 };
@@ -254,8 +262,8 @@ struct lcs_sweep {
 static lcs_status sweep_prepare(lcs_sweep* sw, const std::vector<PlanCfg>& cfgs, uint8_t arm, bool want_fp32) {
   lcs_ctx* ctx = sw->ctx;
   cudaStream_t st = ctx->streams[0];
-  // the previous call's kernels on the other stream may still read the old plans
-  LCS_CUDA(ctx, cudaStreamSynchronize(ctx->streams[1]));
+  // the previous call's kernels on the other streams may still read the old plans
+  for (int i = 1; i < lcs_ctx::N_STREAMS; i++) LCS_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
   lcs_status rc = planset_build(ctx, sw->ps, sw->n_cap, arm, cfgs, want_fp32, st);
   if (rc != LCS_OK) return rc;
   if (!want_fp32 && planset_resolve_kernel(sw->ps, LCS_KERNEL_AUTO, LCS_IQ_CU8) != LCS_KERNEL_TC) {
