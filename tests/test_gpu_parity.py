@@ -287,6 +287,8 @@ def test_tc_edge_shapes(ctx, lcs, oracle):
         (30000, np.arange(-25, 26) * 3000.0, 1, 739e6, 739e6, 1.92e6),          # 51 hypotheses -> 2 chunks
         (30000, np.arange(-32, 32) * 2000.0 + 500.0, 2, 739e6, 739e6, 1.92e6),  # 64 hypotheses -> 2 x 32 (all 96 columns live)
         (30000, np.arange(-35, 35) * 1500.0, 2, 1.8e9, 1.8e9, 1.92e6),          # 70 hypotheses -> 3 chunks
+        (60000, np.arange(-4, 5) * 5000.0, 2, 739e6, 739e6, 1.92e6),            # n_comb = 6: the write-out divides with the division sequence (not in the exact-reciprocal set)
+        (106000, np.arange(-2, 3) * 5000.0, 1, 739e6, 739e6, 1.92e6),           # n_comb = 11, N = 48 single-group layout
     ]
     for i, (n_cap, f, arm, fcr, fcp, fs) in enumerate(cases):
         _tc_vs_oracle(ctx, lcs, oracle, synth_cu8(77 + i, n_cap)[None], f, fcr, fcp, fs, arm)
@@ -620,3 +622,21 @@ def test_sweep_on_a_grid_the_tensor_core_tiling_cannot_hold(ctx, lcs, oracle, ca
             assert abs(a.freq_superfine - b.freq_superfine) < 1e-6
     assert len(got[0]) >= 1 and got[1] == []
     sw.close()
+
+
+def test_long_capture_falls_back_to_the_fp32_correlator(ctx, lcs, oracle):
+    """More than 24 half frames (n_cap = 250000 -> n_comb = 26) exceed the tensor-core kernel's offset table: AUTO serves
+    the 8-bit buffer with the FP32 correlator, an explicit tensor-core plan fails cleanly."""
+    f = np.array([-5000.0, 0.0, 5000.0])
+    cu8 = synth_cu8(321, 250000)
+    plan = ctx.plan(250000, f, 2, 739e6, 739e6, 1.92e6, max_batch=1)
+    assert plan.kernel_for(lcs.IQ_CU8) == lcs.KERNEL_FP32
+    out = plan.run_host_np(cu8[None], lcs.IQ_CU8)
+    ref = oracle.xcorr_pss(cu8_to_c128(cu8), f, 2, 739e6, 739e6, 1.92e6)
+    assert ref["n_comb_xc"] == 26
+    assert rel_err(out["single"][0].transpose(0, 2, 1), ref["single"]) < REL and rel_err(out["pow"][0], ref["pow"]) < REL
+    plan.close()
+    tcp = ctx.plan(250000, f, 2, 739e6, 739e6, 1.92e6, max_batch=1, kernel=lcs.KERNEL_TC)
+    with pytest.raises(lcs.LcsError):
+        tcp.run_host_np(cu8[None], lcs.IQ_CU8)
+    tcp.close()
