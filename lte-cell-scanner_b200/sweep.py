@@ -97,3 +97,56 @@ def sweep_batched(fc_all, iq_mine, batch_search_fn, new_cell, dedup_fn, dist=Non
     idx = shard(len(fc_all), rank, world)
     res = batch_search_fn(iq_mine, [fc_all[i] for i in idx]) if idx else []
     return gather_dedup(list(zip(idx, res)), new_cell, dedup_fn, dist, device, max_cells_per_rank)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Latency mode (secondary partitioning): ONE capture buffer, the frequency hypotheses split across the ranks.
+# Every rank runs xcorr_pss on its slice of f_search_set; xc_peak_freq (searcher.cpp:353-383: largest power over f, FIRST
+# maximum wins) is finished by one all_reduce(MAX) over packed 64-bit keys {float bits of the power, ~global f index}:
+# the power is a non-negative float, so its bit pattern orders like the value, and the complemented index makes the
+# lowest f win among equal powers - exactly the strict '>' scan of the reference.
+# ---------------------------------------------------------------------------------------------------------------------
+def f_slices(n_f, world):
+    """Contiguous, balanced slices of the hypothesis list (rank r gets [lo, hi))."""
+    base, extra = divmod(n_f, world)
+    lo = [r * base + min(r, extra) for r in range(world)]
+    return [(lo[r], lo[r] + base + (1 if r < extra else 0)) for r in range(world)]
+
+
+def pack_pow_frq(pow_f32, frq_local, f_lo):
+    """pow_f32: float32 [3][9600] (the collapsed power is a float widened to double in the reference, :380);
+    frq_local: int32 index inside this rank's slice.  Returns int64 keys."""
+    bits = np.ascontiguousarray(pow_f32, np.float32).view(np.uint32).astype(np.int64)
+    idx = (np.asarray(frq_local, np.int64) + f_lo)
+    return (bits << 32) | (0xFFFFFFFF - idx)
+
+
+def unpack_pow_frq(keys):
+    keys = np.asarray(keys, np.int64)
+    bits = (keys >> 32).astype(np.uint32)
+    frq = (0xFFFFFFFF - (keys & 0xFFFFFFFF)).astype(np.int32)
+    return bits.view(np.float32).astype(np.float64), frq
+
+
+def xcorr_pss_fsplit(run_slice, f_set, dist=None, device=None):
+    """run_slice(f_subset) -> dict(pow [3][9600] float64, frq [3][9600] int32, sp_incoherent) for this rank's
+    hypotheses (an empty slice returns None).  Returns (pow, frq, sp_incoherent) of the whole grid on every rank."""
+    import torch
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    lo, hi = f_slices(len(f_set), world)[rank]
+    out = run_slice(f_set[lo:hi]) if hi > lo else None
+    if out is None:
+        keys = np.full((3, 9600), -1, np.int64)          # below every real key (powers are >= 0)
+        spi = None
+    else:
+        keys = pack_pow_frq(out["pow"].astype(np.float32), out["frq"], lo)
+        spi = out["sp_incoherent"]
+    if dist is not None:
+        t = torch.from_numpy(keys)
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        keys = t.cpu().numpy()
+    pw, frq = unpack_pow_frq(keys)
+    return pw, frq, spi

@@ -80,3 +80,52 @@ def test_shard_and_pack_roundtrip():
 
 def test_two_rank_sweep_equals_single_process():
     assert _run(2) == _run(1)
+
+
+def test_fsplit_pack_orders_like_the_reference_argmax():
+    """Latency mode: the packed {power bits, ~f index} keys reduce with MAX to the reference's xc_peak_freq result (largest
+    power, FIRST maximum among equals) for any split of the hypothesis list."""
+    sys.path.insert(0, os.path.join(ROOT, "lte-cell-scanner_b200"))
+    import sweep
+    rng = np.random.default_rng(4)
+    n_f = 37
+    inc = rng.random((3, 9600, n_f)).astype(np.float32)
+    inc[:, ::7, 5] = inc[:, ::7, 20] = 2.0              # exact ties: the lower index must win
+    inc[0, 3, :] = 0.0                                  # all-zero column: index 0
+    ref_frq = inc.argmax(axis=2).astype(np.int32)       # numpy argmax returns the first maximum, like the strict '>' scan
+    ref_pow = inc.max(axis=2).astype(np.float64)
+    for world in (1, 2, 3, 8, 40):
+        keys = np.full((3, 9600), -1, np.int64)
+        for lo, hi in sweep.f_slices(n_f, world):
+            if hi == lo:
+                continue
+            sl = inc[:, :, lo:hi]
+            k = sweep.pack_pow_frq(sl.max(axis=2), sl.argmax(axis=2), lo)
+            keys = np.maximum(keys, k)                  # what all_reduce(MAX) computes
+        pw, frq = sweep.unpack_pow_frq(keys)
+        assert np.array_equal(frq, ref_frq) and np.array_equal(pw, ref_pow), world
+
+
+def test_fsplit_two_ranks_gloo():
+    code = textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, os.path.join(%(root)r, "lte-cell-scanner_b200"))
+        import numpy as np, torch.distributed as dist
+        import sweep
+        dist.init_process_group("gloo")
+        rng = np.random.default_rng(9)
+        inc = rng.random((3, 9600, 11)).astype(np.float32)
+        f = np.arange(11) * 5000.0
+        def run(fsub):
+            lo = int(round(fsub[0] / 5000.0)); hi = lo + len(fsub)
+            sl = inc[:, :, lo:hi]
+            return dict(pow=sl.max(axis=2).astype(np.float64), frq=sl.argmax(axis=2).astype(np.int32), sp_incoherent=np.zeros(9600))
+        pw, frq, _ = sweep.xcorr_pss_fsplit(run, f, dist=dist)
+        assert np.array_equal(frq, inc.argmax(axis=2)) and np.array_equal(pw, inc.max(axis=2).astype(np.float64))
+        if dist.get_rank() == 0:
+            print("FSPLIT OK")
+        dist.destroy_process_group()
+    """) % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29619", "--no-python", sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "FSPLIT OK" in out.stdout, out.stderr[-2000:]
