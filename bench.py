@@ -619,6 +619,16 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": alg_bytes / k_avg_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        if kernel_used == "xcorr_fold_tc" and args.workload == "search":
+            # executed int8 operations: 38 tiles x 15 half frames x 2 sub-tiles x 2 parts x 2 jobs per buffer, 9 UTCIMMA of
+            # M=128, N=144, K=32 B per job; against the rate a loop of nothing but these instructions sustains on all SMs
+            # (tools/microbench/umma_sustained.cu, profiles/r02_umma_sustained_microbench.txt)
+            ops = B * 38 * 15 * 2 * 2 * 2 * 9 * (2.0 * 128 * 144 * 32)
+            pops = ops / k_avg_s / 1e15
+            ceil_pops = 3.65 if (clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] < 1750) else 4.1
+            roof.update({"executed_int8_pops": pops, "pure_mma_ceiling_int8_pops": ceil_pops,
+                         "pure_mma_ceiling_note": "4.1 POP/s for a burst at ~1.83 GHz, 3.65 POP/s power-capped at ~1.63 GHz (measured, profiles/r02_umma_sustained_microbench.txt); chosen by the SM clock sampled during this run",
+                         "frac_of_pure_mma_ceiling": pops / ceil_pops})
         roof.update({"traffic": ncu_traffic(kernel_used, B), "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, scaled to this batch)",
                      "kernel": kernel_used, "kernel_avg_ms": k_avg_s * 1e3, "kernel_launches": kernel_n,
                      "kernel_share_of_step": kernel_ms / ms, "alg_bytes_per_launch": alg_bytes,
