@@ -3,6 +3,7 @@
 # Usage (repo root, under gpurun):  bash tools/gpu_prof_r2.sh <tag>
 TAG=${1:-r02}
 mkdir -p gpurun_out
+[ -f lte-cell-scanner_b200/liblcs_b200_prof.so ] || make -C lte-cell-scanner_b200 prof > /dev/null 2>&1   # instrumented build (stage counters)
 LCS_B200_LIB=$PWD/lte-cell-scanner_b200/liblcs_b200_prof.so LCS_TC_PROF=1 timeout 300 python tools/gpu_tc_prof.py 384 > gpurun_out/tc_stage_waits_$TAG.txt 2>&1
 cat gpurun_out/tc_stage_waits_$TAG.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
