@@ -280,14 +280,19 @@ xcorr_fold_tc_kernel(const __grid_constant__ TcParams p) {
       const int smin = __ldg(&p.geo[s.r.pp].smin[s.m]);
       const uint64_t z = iq_lo + 2ull * ((uint64_t)s.r.b * p.n_cap + (uint64_t)(s.r.p0 + (int)(tc::NT * s.k) + smin));
       const uint64_t zal = z & ~15ull;
+      // Bytes past the end of the allocation are never needed by a position that is written out (planset.cu checks the
+      // fold offsets), so the copy is clamped to the allocation and the rest of the staging buffer keeps its previous
+      // contents.  The bulk copy moves whole 16-byte chunks: when the allocation ends inside a chunk, its last (< 16) bytes
+      // - the final samples of the last capture buffer, which an extreme k_factor can make necessary - are copied by lanes.
+      uint32_t bytes = 0, rem = 0;
+      if (zal < iq_hi) {
+        const uint64_t avail = iq_hi - zal;
+        const uint64_t left = avail & ~15ull;
+        if (left < (uint64_t)(tc::RAW_BYTES - 16)) { bytes = (uint32_t)left; rem = (uint32_t)(avail - left); }
+        else bytes = (uint32_t)(tc::RAW_BYTES - 16);
+      }
+      if ((uint32_t)lane < rem) smem[SM::RAW + rs * tc::RAW_BYTES + bytes + lane] = __ldg(reinterpret_cast<const uint8_t*>(zal) + bytes + lane);
       if (lane == 0) {
-        // bytes past the end of the allocation are never needed by a position that is written out (planset.cu checks the
-        // fold offsets): the tail of the staging buffer just keeps its previous contents
-        uint32_t bytes = 0;
-        if (zal < iq_hi) {
-          const uint64_t left = (iq_hi - zal) & ~15ull;
-          bytes = left < (uint64_t)(tc::RAW_BYTES - 16) ? (uint32_t)left : (uint32_t)(tc::RAW_BYTES - 16);
-        }
         if (bytes) {
           mbar_arrive_expect_tx(BAR_RAW + 8 * rs, bytes);
           bulk_g2s(raw_addr + rs * tc::RAW_BYTES, reinterpret_cast<const void*>(zal), bytes, BAR_RAW + 8 * rs);

@@ -640,3 +640,18 @@ def test_long_capture_falls_back_to_the_fp32_correlator(ctx, lcs, oracle):
     with pytest.raises(lcs.LcsError):
         tcp.run_host_np(cu8[None], lcs.IQ_CU8)
     tcp.close()
+
+
+def test_tc_last_samples_of_the_last_buffer(ctx, lcs, oracle):
+    """An extreme k_factor (fc_programmed = fc_requested / 2.00677) pushes the last fold offset to the limit the plan accepts:
+    the very last sample of the capture buffer enters the correlation, and with n_cap = 29001 it sits in a partial 16-byte
+    chunk at the end of the allocation (the TMA staging copies whole chunks; the tail is copied by lanes)."""
+    n_cap = 29001
+    fcr = 739e6
+    fcp = fcr / 2.00677
+    f = np.array([0.0])
+    assert int(np.rint(9600 * (fcr / fcp))) + 9599 == n_cap - 136 - 1
+    cu8 = synth_cu8(77, n_cap)
+    cu8[-40:] = 255                                  # make the tail samples matter
+    for batch in (1, 2):
+        _tc_vs_oracle(ctx, lcs, oracle, np.stack([cu8] * batch), f, fcr, fcp, 1.92e6)
