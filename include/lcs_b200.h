@@ -105,7 +105,9 @@ uint16_t lcs_xcorr_plan_n_comb_sp(const lcs_xcorr_plan* plan);
 int lcs_xcorr_plan_kernel(const lcs_xcorr_plan* plan, int iq_format);   /* kernel AUTO resolves to */
 
 /* Device-resident, batched, asynchronous on `stream` (a cudaStream_t; NULL = default stream).
- *   d_iq            [batch][n_cap] samples in iq_format (CF32 or CU8), device memory
+ *   d_iq            [batch][n_cap] samples in iq_format (CF32, CU8 or C128), device memory.  The tensor-core correlator
+ *                   stages raw bytes with 16-byte bulk copies: a CU8 pointer that is not 16-byte aligned is served by the
+ *                   FP32 correlator under LCS_KERNEL_AUTO and rejected under LCS_KERNEL_TC (buffer strides may be odd)
  *   d_single_planar [batch][3][n_f][9600] float  (xc_incoherent_single, f-major "planar" layout)
  *   d_pow           [batch][3][9600] double,  d_frq [batch][3][9600] int32   (row-major (t,idx))
  *   d_sp_incoherent [batch][9600] double
