@@ -276,3 +276,18 @@ def test_three_instruction_division_matches_ieee_on_samples():
         e = (x.astype(np.float64) - d.astype(np.float64) * q.astype(np.float64)).astype(np.float32)   # fma(-n, q, x): exact product, one rounding
         q2 = (e.astype(np.float64) * r.astype(np.float64) + q.astype(np.float64)).astype(np.float32)
         assert np.array_equal(q2, (x / d).astype(np.float32)), n
+
+
+def test_library_contains_blackwell_native_instructions(lcs):
+    """The shipped liblcs_b200.so must carry the tcgen05 / TMEM / TMA code paths (SASS mnemonics of B200_PROFILING.md):
+    UTCIMMA = tcgen05.mma kind::i8, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (1-D TMA)."""
+    import os
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", lcs.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    for mnemonic in ("UTCIMMA", "LDTM", "UTCBAR", "UBLKCP"):
+        assert sass.count(mnemonic) > 0, mnemonic
+    assert "sm_100a" in subprocess.run([exe, "-lelf", lcs.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
